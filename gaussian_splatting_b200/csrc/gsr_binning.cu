@@ -1,0 +1,270 @@
+// gsr_binning.cu — (gaussian, tile) pair generation, depth sort, tile ranges and the
+// packed per-pair record stream the tile renderers consume.
+//
+// Replaces the reference's src/tile_culling.cu:124-340: instead of an fp64 key
+// z + (max_z+1)*tile sorted by torch::sort plus an index_select, each pair gets
+// the 64-bit key (tile << 32 | order-preserving bits of z) and is sorted together
+// with its gaussian id by one cub::DeviceRadixSort over only the significant bits.
+// Order is identical: (tile, z) ascending, ties by gaussian index (radix sort is
+// stable and pairs are emitted in gaussian order) — SURVEY.md Q12.
+#include <cub/cub.cuh>
+
+#include "gsr_common.cuh"
+#include "gsr_math.cuh"
+#include "gsr_record.cuh"
+
+namespace gsr {
+
+constexpr int BIN_THREADS = 256;
+
+// tiles overlapped by one gaussian.  Reference: src/tile_culling.cu:139-176.
+// When keys != nullptr also emits the pairs at keys[base...].
+__device__ __forceinline__ int walk_tiles(const Obb& o, float u, float v, int ntx, int nty,
+                                          uint32_t zkey, uint32_t id, uint64_t* __restrict__ keys,
+                                          uint32_t* __restrict__ ids, int64_t base) {
+    int x0, x1, y0, y1;
+    tile_window(u, v, o.radius_tiles, ntx, nty, x0, x1, y0, y1);
+    int n = 0;
+    for (int tx = x0; tx < x1; ++tx) {
+        const float left = __fmul_rn(__int2float_rn(tx), 16.0f);
+        const float right = __fmul_rn(__int2float_rn(tx + 1), 16.0f);
+        for (int ty = y0; ty < y1; ++ty) {
+            const float top = __fmul_rn(__int2float_rn(ty), 16.0f);
+            const float bottom = __fmul_rn(__int2float_rn(ty + 1), 16.0f);
+            if (obb_hits_tile(o, left, right, top, bottom)) {
+                if (keys) {
+                    const uint32_t tile = (uint32_t)(ty * ntx + tx);
+                    keys[base + n] = ((uint64_t)tile << 32) | zkey;
+                    ids[base + n] = id;
+                }
+                ++n;
+            }
+        }
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+    k_count_tiles(int N, const float* __restrict__ uvs, const float* __restrict__ conic, int ntx, int nty,
+                  float mh, int32_t* __restrict__ counts) {
+    const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (i >= N) return;
+    const float u = uvs[i * 2], v = uvs[i * 2 + 1];
+    Obb o;
+    compute_obb(u, v, __fadd_rn(conic[i * 3], 0.25f), __fmul_rn(conic[i * 3 + 1], 0.5f),
+                __fadd_rn(conic[i * 3 + 2], 0.25f), mh, o);
+    counts[i] = walk_tiles(o, u, v, ntx, nty, 0u, 0u, nullptr, nullptr, 0);
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+    k_emit_pairs_api(int N, const float* __restrict__ uvs, const float* __restrict__ xyz_cam,
+                     const float* __restrict__ conic, int ntx, int nty, float mh,
+                     const int32_t* __restrict__ offsets, uint64_t* __restrict__ keys,
+                     uint32_t* __restrict__ ids) {
+    const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (i >= N) return;
+    if (offsets[i + 1] == offsets[i]) return;
+    const float u = uvs[i * 2], v = uvs[i * 2 + 1];
+    Obb o;
+    compute_obb(u, v, __fadd_rn(conic[i * 3], 0.25f), __fmul_rn(conic[i * 3 + 1], 0.5f),
+                __fadd_rn(conic[i * 3 + 2], 0.25f), mh, o);
+    walk_tiles(o, u, v, ntx, nty, depth_key(xyz_cam[i * 3 + 2]), (uint32_t)i, keys, ids, offsets[i]);
+}
+
+// fused path: the record already holds a, 2b, c (b = 0.5 * 2b is exact)
+__global__ void __launch_bounds__(BIN_THREADS)
+    k_emit_pairs_fused(int N, const float* __restrict__ records,
+                       const uint32_t* __restrict__ zkey, const uint8_t* __restrict__ visible,
+                       const uint64_t* __restrict__ scan, int ntx, int nty, float mh,
+                       uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
+                       int32_t* __restrict__ vis_idx, float* __restrict__ uv_compact) {
+    const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (i >= N) return;
+    if (!visible[i]) return;
+    const uint64_t incl = scan[i];
+    const uint64_t prev = (i > 0) ? scan[i - 1] : 0ull;
+    const uint32_t rank = (uint32_t)(prev >> 32);
+    const uint32_t cnt = (uint32_t)(incl & 0xffffffffu) - (uint32_t)(prev & 0xffffffffu);
+    const float u = records[(size_t)i * REC + R_U], v = records[(size_t)i * REC + R_V];
+    vis_idx[rank] = i;
+    uv_compact[rank * 2 + 0] = u;
+    uv_compact[rank * 2 + 1] = v;
+    if (cnt == 0) return;
+    Obb o;
+    const float* r = records + (size_t)i * REC;
+    compute_obb(u, v, r[R_A], __fmul_rn(r[R_B2], 0.5f), r[R_C], mh, o);
+    walk_tiles(o, u, v, ntx, nty, zkey[i], (uint32_t)i, keys, ids, (int64_t)(prev & 0xffffffffu));
+}
+
+// tile_ranges[t] = first sorted position whose tile id >= t  (ranges[n_tiles] = P).
+// One block stages BIN_THREADS+1 tile ids through shared memory; each position closes the
+// ranges of every tile id in (tile[p-1], tile[p]].
+__global__ void __launch_bounds__(BIN_THREADS)
+    k_tile_ranges(int P, int n_tiles, const uint64_t* __restrict__ keys, int32_t* __restrict__ ranges) {
+    __shared__ int32_t s_tile[BIN_THREADS + 1];
+    const int p0 = blockIdx.x * BIN_THREADS;
+    const int p = p0 + threadIdx.x;
+    if (p < P) s_tile[threadIdx.x + 1] = (int32_t)(keys[p] >> 32);
+    if (threadIdx.x == 0) s_tile[0] = (p0 > 0) ? (int32_t)(keys[p0 - 1] >> 32) : -1;
+    __syncthreads();
+    if (p >= P) return;
+    const int cur = s_tile[threadIdx.x + 1];
+    const int prev = s_tile[threadIdx.x];
+    for (int t = prev + 1; t <= cur; ++t) ranges[t] = p;
+    if (p == P - 1)
+        for (int t = cur + 1; t <= n_tiles; ++t) ranges[t] = P;
+}
+
+__global__ void k_fill_i32(int n, int32_t* __restrict__ out, int32_t value) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = value;
+}
+
+__global__ void __launch_bounds__(BIN_THREADS) k_ids_to_i32(int P, const uint32_t* __restrict__ in,
+                                                            int32_t* __restrict__ out) {
+    const int p = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (p < P) out[p] = (int32_t)in[p];
+}
+
+// one 48-byte record per pair, three 16-byte lanes per record: thread -> (pair, lane)
+__global__ void __launch_bounds__(BIN_THREADS)
+    k_gather_records(int P, const uint32_t* __restrict__ ids, const float4* __restrict__ rec,
+                     float4* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (t >= (int64_t)P * 3) return;
+    const int p = (int)(t / 3), lane = (int)(t % 3);
+    out[t] = __ldg(rec + (size_t)ids[p] * 3 + lane);
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+    k_pack_records(int P, const int32_t* __restrict__ idx, const float* __restrict__ uvs,
+                   const float* __restrict__ opacity, const float* __restrict__ rgb,
+                   const float* __restrict__ conic, float* __restrict__ out) {
+    const int p = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (p >= P) return;
+    const int g = idx[p];
+    float rec[REC];
+    make_record(uvs[g * 2], uvs[g * 2 + 1], conic[g * 3], conic[g * 3 + 1], conic[g * 3 + 2], opacity[g],
+                rgb[g * 3], rgb[g * 3 + 1], rgb[g * 3 + 2], rec);
+    float4* o = reinterpret_cast<float4*>(out + (size_t)p * REC);
+    o[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+    o[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+    o[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+}
+
+static inline int sort_end_bit(int n_tiles) {
+    int bits = 0;
+    while ((1 << bits) < n_tiles) ++bits;
+    return 32 + (bits > 0 ? bits : 1);
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace gsr
+
+using namespace gsr;
+
+#define BGRID(n) dim3((unsigned)(((int64_t)(n) + BIN_THREADS - 1) / BIN_THREADS)), dim3(BIN_THREADS), 0, st
+
+extern "C" {
+
+size_t gsr_binning_count_temp_bytes(int N) {
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum((void*)nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, N + 1);
+    return align256(scan_bytes) + align256(sizeof(int32_t) * (size_t)(N + 1));
+}
+
+int gsr_binning_count(int N, const float* uvs, const float* conic, int ntx, int nty, float mh,
+                      int32_t* offsets, void* temp, size_t temp_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N < 0 || temp_bytes < gsr_binning_count_temp_bytes(N)) return GSR_ERR_BAD_ARG;
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum((void*)nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, N + 1);
+    int32_t* counts = reinterpret_cast<int32_t*>((char*)temp + align256(scan_bytes));
+    // counts has N+1 entries, the last one 0, so the exclusive scan yields offsets[N] == P
+    k_fill_i32<<<1, 1, 0, st>>>(1, counts + N, 0);
+    if (N > 0) k_count_tiles<<<BGRID(N)>>>(N, uvs, conic, ntx, nty, mh, counts);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(temp, scan_bytes, counts, offsets, N + 1, st);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+
+size_t gsr_sort_pairs_temp_bytes(int P) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, b, (uint64_t*)nullptr, (uint64_t*)nullptr,
+                                    (uint32_t*)nullptr, (uint32_t*)nullptr, P > 0 ? P : 1, 0, 64);
+    return align256(b);
+}
+
+int gsr_sort_pairs(int P, int n_tiles, const uint64_t* keys_in, const uint32_t* ids_in,
+                   uint64_t* keys_out, uint32_t* ids_out, void* temp, size_t temp_bytes, void* stream) {
+    if (P <= 0) return GSR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t b = temp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, b, keys_in, keys_out, ids_in, ids_out, P, 0,
+                                                    sort_end_bit(n_tiles), st);
+    return (int)e;
+}
+
+int gsr_tile_ranges(int P, int n_tiles, const uint64_t* keys_sorted, int32_t* ranges, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P <= 0) {
+        k_fill_i32<<<BGRID(n_tiles + 1)>>>(n_tiles + 1, ranges, 0);
+    } else {
+        k_tile_ranges<<<BGRID(P)>>>(P, n_tiles, keys_sorted, ranges);
+    }
+    return (int)cudaGetLastError();
+}
+
+size_t gsr_binning_sort_temp_bytes(int P) {
+    const size_t p = (size_t)(P > 0 ? P : 1);
+    return gsr_sort_pairs_temp_bytes(P) + 2 * align256(8 * p) + 2 * align256(4 * p);
+}
+
+int gsr_binning_emit_sort(int N, int P, const float* uvs, const float* xyz_cam, const float* conic,
+                          int ntx, int nty, float mh, const int32_t* offsets, int32_t* sorted_idx,
+                          int32_t* ranges, void* temp, size_t temp_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_tiles = ntx * nty;
+    if (temp_bytes < gsr_binning_sort_temp_bytes(P)) return GSR_ERR_BAD_ARG;
+    if (P <= 0) return gsr_tile_ranges(0, n_tiles, nullptr, ranges, stream);
+    const size_t p = (size_t)P;
+    char* base = (char*)temp;
+    const size_t sort_bytes = gsr_sort_pairs_temp_bytes(P);
+    uint64_t* keys_a = (uint64_t*)(base + sort_bytes);
+    uint64_t* keys_b = (uint64_t*)((char*)keys_a + align256(8 * p));
+    uint32_t* ids_a = (uint32_t*)((char*)keys_b + align256(8 * p));
+    uint32_t* ids_b = (uint32_t*)((char*)ids_a + align256(4 * p));
+    k_emit_pairs_api<<<BGRID(N)>>>(N, uvs, xyz_cam, conic, ntx, nty, mh, offsets, keys_a, ids_a);
+    int rc = gsr_sort_pairs(P, n_tiles, keys_a, ids_a, keys_b, ids_b, temp, sort_bytes, stream);
+    if (rc) return rc;
+    k_ids_to_i32<<<BGRID(P)>>>(P, ids_b, sorted_idx);
+    return gsr_tile_ranges(P, n_tiles, keys_b, ranges, stream);
+}
+
+int gsr_emit_pairs(int N, const float* records, const uint32_t* depth_key,
+                   const uint8_t* visible, const uint64_t* scan, int ntx, int nty, float mh,
+                   uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0) return GSR_OK;
+    k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, keys,
+                                     ids, vis_idx, uv_compact);
+    return (int)cudaGetLastError();
+}
+
+int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, float* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P <= 0) return GSR_OK;
+    k_gather_records<<<BGRID((int64_t)P * 3)>>>(P, ids_sorted, (const float4*)records, (float4*)out);
+    return (int)cudaGetLastError();
+}
+
+int gsr_pack_records(int P, const int32_t* idx, const float* uvs, const float* opacity, const float* rgb,
+                     const float* conic, float* records, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P <= 0) return GSR_OK;
+    k_pack_records<<<BGRID(P)>>>(P, idx, uvs, opacity, rgb, conic, records);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+// gsr_preprocess.cu — the fused per-Gaussian stage behind rasterize().
+//
+// One kernel replaces, for every Gaussian of the scene, the reference's chain
+//   transform_points_torch        splat_py/utils.py:60-72
+//   CameraPointProjection         src/projection.cu:8-19
+//   frustum cull + 8 mask gathers splat_py/rasterize.py:33-75
+//   sigmoid(opacity)              splat_py/rasterize.py:60-62
+//   ComputeSigmaWorld             src/projection.cu:56-109
+//   ComputeProjectionJacobian     src/projection.cu:154-175
+//   ComputeConic                  src/projection.cu:213-257
+//   cat(rgb, sh) + PrecomputeRGBFromSH   splat_py/rasterize.py:89-93, src/precompute_sh.cu:7-58
+//   compute_num_splats_kernel     src/tile_culling.cu:124-177
+// and writes one 48-byte splat record, a depth key, a visibility flag and the
+// tiles-touched count per Gaussian.  No Sigma_world / J intermediates reach HBM.
+// The backward kernel is the fused VJP of the same chain.
+#include <cub/cub.cuh>
+
+#include "gsr_common.cuh"
+#include "gsr_math.cuh"
+#include "gsr_math_bwd.cuh"
+#include "gsr_record.cuh"
+
+namespace gsr {
+
+constexpr int PRE_THREADS = 256;
+
+struct ViewConsts {
+    float T[16];
+    float K[9];
+    float cam[3];  // camera centre in world frame = inverse(camera_T_world)[:3, 3]
+};
+
+// last column of inverse(T) by Gauss-Jordan with partial pivoting in fp64 (one thread)
+__device__ void camera_centre(const float* __restrict__ T, float* __restrict__ cam) {
+    double A[4][5];
+    for (int r = 0; r < 4; ++r) {
+        for (int c = 0; c < 4; ++c) A[r][c] = (double)T[r * 4 + c];
+        A[r][4] = (r == 3) ? 1.0 : 0.0;
+    }
+    for (int col = 0; col < 4; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 4; ++r)
+            if (fabs(A[r][col]) > fabs(A[piv][col])) piv = r;
+        for (int c = 0; c < 5; ++c) {
+            const double t = A[col][c];
+            A[col][c] = A[piv][c];
+            A[piv][c] = t;
+        }
+        const double inv = 1.0 / A[col][col];
+        for (int c = 0; c < 5; ++c) A[col][c] *= inv;
+        for (int r = 0; r < 4; ++r) {
+            if (r == col) continue;
+            const double f = A[r][col];
+            for (int c = 0; c < 5; ++c) A[r][c] -= f * A[col][c];
+        }
+    }
+    cam[0] = (float)A[0][4];
+    cam[1] = (float)A[1][4];
+    cam[2] = (float)A[2][4];
+}
+
+__device__ __forceinline__ void load_view(const float* __restrict__ T, const float* __restrict__ K,
+                                          ViewConsts& vc) {
+    // called by one thread per block, result lives in shared memory
+    for (int k = 0; k < 16; ++k) vc.T[k] = T[k];
+    for (int k = 0; k < 9; ++k) vc.K[k] = K[k];
+    camera_centre(vc.T, vc.cam);
+}
+
+// SH -> RGB exactly as src/precompute_sh.cu:29-56 evaluates it on cat(rgb_dc, sh_rest)
+template <int N_SH>
+__device__ __forceinline__ void sh_rgb_fused(const float* __restrict__ dc, const float* __restrict__ rest,
+                                             float px, float py, float pz, const float* cam,
+                                             float* __restrict__ out) {
+    if (N_SH == 1) {
+        out[0] = dc[0]; out[1] = dc[1]; out[2] = dc[2];
+        return;
+    }
+    float dx, dy, dz, Y[N_SH];
+    view_dir<float>(px, py, pz, cam[0], cam[1], cam[2], dx, dy, dz);
+    sh_basis<float, N_SH>(dx, dy, dz, Y);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float acc = __fmaf_rn(Y[0], dc[c], 0.0f);
+#pragma unroll
+        for (int k = 1; k < N_SH; ++k) acc = __fmaf_rn(Y[k], rest[c * (N_SH - 1) + (k - 1)], acc);
+        out[c] = __fmul_rn(acc, GSR_RSH0);
+    }
+}
+
+template <int N_SH, bool HAS_SH>
+__global__ void __launch_bounds__(PRE_THREADS)
+    k_preprocess_fwd(int N, const float* __restrict__ xyz, const float* __restrict__ quat,
+                     const float* __restrict__ scale, const float* __restrict__ opa_logit,
+                     const float* __restrict__ rgb_dc, const float* __restrict__ sh_rest,
+                     const float* __restrict__ Tdev, const float* __restrict__ Kdev, float width,
+                     float height, float near_t, float far_t, float pad, float mh, int ntx, int nty,
+                     float* __restrict__ records, uint32_t* __restrict__ zkey,
+                     uint8_t* __restrict__ visible, uint64_t* __restrict__ packed) {
+    __shared__ ViewConsts vc;
+    if (threadIdx.x == 0) load_view(Tdev, Kdev, vc);
+    __syncthreads();
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    if (i >= N) return;
+
+    const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
+    float px, py, pz, u, v;
+    transform_point<float>(vc.T, x, y, z, px, py, pz);
+    project_uv<float>(px, py, pz, vc.K[0], vc.K[2], vc.K[4], vc.K[5], u, v);
+    // splat_py/rasterize.py:38-49 (strict compares, fp32)
+    const bool culled = (pz < near_t) | (pz > far_t) | (u < -pad) | (u > width + pad) | (v < -pad) |
+                        (v > height + pad);
+    zkey[i] = depth_key(pz);
+    // NaN coordinates compare false everywhere and would survive; the reference aborts on them
+    // (splat_py/tile_culling.py:15-18) — treat as culled instead.
+    const bool vis = !culled && (pz == pz) && (u == u) && (v == v);
+    visible[i] = vis ? 1 : 0;
+    if (!vis) {
+        packed[i] = 0ull;
+        return;
+    }
+    float S6[6], S9[9], J[6], W[9], conic[3];
+    sigma_world<float>(quat[i * 4 + 0], quat[i * 4 + 1], quat[i * 4 + 2], quat[i * 4 + 3], scale[i * 3 + 0],
+                       scale[i * 3 + 1], scale[i * 3 + 2], S6);
+    sym6_to_full(S6, S9);
+    proj_jacobian<float>(px, py, pz, vc.K[0], vc.K[4], J);
+    W[0] = vc.T[0]; W[1] = vc.T[1]; W[2] = vc.T[2];
+    W[3] = vc.T[4]; W[4] = vc.T[5]; W[5] = vc.T[6];
+    W[6] = vc.T[8]; W[7] = vc.T[9]; W[8] = vc.T[10];
+    conic_from<float>(S9, J, W, conic, nullptr);
+
+    const float opa = sigmoid_torch(opa_logit[i]);
+    float dc[3] = {rgb_dc[i * 3 + 0], rgb_dc[i * 3 + 1], rgb_dc[i * 3 + 2]};
+    float col[3];
+    if (HAS_SH) {
+        float rest[3 * (N_SH - 1) + 1];
+        const float* src = sh_rest + (size_t)i * 3 * (N_SH - 1);
+#pragma unroll
+        for (int k = 0; k < 3 * (N_SH - 1); ++k) rest[k] = src[k];
+        sh_rgb_fused<N_SH>(dc, rest, x, y, z, vc.cam, col);
+    } else {
+        col[0] = dc[0]; col[1] = dc[1]; col[2] = dc[2];
+    }
+    float rec[REC];
+    make_record(u, v, conic[0], conic[1], conic[2], opa, col[0], col[1], col[2], rec);
+    float4* o = reinterpret_cast<float4*>(records + (size_t)i * REC);
+    o[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+    o[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+    o[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+
+    // tiles touched (src/tile_culling.cu:139-176)
+    Obb ob;
+    compute_obb(u, v, rec[R_A], __fmul_rn(rec[R_B2], 0.5f), rec[R_C], mh, ob);
+    int x0, x1, y0, y1, cnt = 0;
+    tile_window(u, v, ob.radius_tiles, ntx, nty, x0, x1, y0, y1);
+    for (int tx = x0; tx < x1; ++tx) {
+        const float left = __fmul_rn(__int2float_rn(tx), 16.0f);
+        const float right = __fmul_rn(__int2float_rn(tx + 1), 16.0f);
+        for (int ty = y0; ty < y1; ++ty) {
+            const float top = __fmul_rn(__int2float_rn(ty), 16.0f);
+            const float bottom = __fmul_rn(__int2float_rn(ty + 1), 16.0f);
+            cnt += obb_hits_tile(ob, left, right, top, bottom) ? 1 : 0;
+        }
+    }
+    packed[i] = (1ull << 32) | (uint64_t)(uint32_t)cnt;
+}
+
+// Fused VJP.  g_rgb/g_opa/g_uv/g_conic are the per-Gaussian sums produced by the render backward
+// (indexed by original gaussian).  Order of the chain: SURVEY.md Appendix A "Per-Gaussian backward".
+template <int N_SH, bool HAS_SH>
+__global__ void __launch_bounds__(PRE_THREADS)
+    k_preprocess_bwd(int N, const float* __restrict__ xyz, const float* __restrict__ quat,
+                     const float* __restrict__ scale, const float* __restrict__ opa_logit,
+                     const float* __restrict__ Tdev, const float* __restrict__ Kdev,
+                     const uint8_t* __restrict__ visible, const float* __restrict__ g_rgb,
+                     const float* __restrict__ g_opa, const float* __restrict__ g_uv,
+                     const float* __restrict__ g_conic, float* __restrict__ o_xyz,
+                     float* __restrict__ o_quat, float* __restrict__ o_scale, float* __restrict__ o_opa,
+                     float* __restrict__ o_dc, float* __restrict__ o_sh) {
+    __shared__ ViewConsts vc;
+    if (threadIdx.x == 0) load_view(Tdev, Kdev, vc);
+    __syncthreads();
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    if (i >= N) return;
+    constexpr int NR = N_SH - 1;
+    if (!visible[i]) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { o_xyz[i * 3 + k] = 0.f; o_scale[i * 3 + k] = 0.f; o_dc[i * 3 + k] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o_quat[i * 4 + k] = 0.f;
+        o_opa[i] = 0.f;
+        if (HAS_SH) {
+            float* dst = o_sh + (size_t)i * 3 * NR;
+#pragma unroll
+            for (int k = 0; k < 3 * NR; ++k) dst[k] = 0.f;
+        }
+        return;
+    }
+    const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
+    float px, py, pz;
+    transform_point<float>(vc.T, x, y, z, px, py, pz);
+    const float qw = quat[i * 4 + 0], qx = quat[i * 4 + 1], qy = quat[i * 4 + 2], qz = quat[i * 4 + 3];
+    const float s0 = scale[i * 3 + 0], s1 = scale[i * 3 + 1], s2 = scale[i * 3 + 2];
+    float S6[6], S9[9], J[6], W[9];
+    sigma_world<float>(qw, qx, qy, qz, s0, s1, s2, S6);
+    sym6_to_full(S6, S9);
+    proj_jacobian<float>(px, py, pz, vc.K[0], vc.K[4], J);
+    W[0] = vc.T[0]; W[1] = vc.T[1]; W[2] = vc.T[2];
+    W[3] = vc.T[4]; W[4] = vc.T[5]; W[5] = vc.T[6];
+    W[6] = vc.T[8]; W[7] = vc.T[9]; W[8] = vc.T[10];
+
+    const float gc[3] = {g_conic[i * 3 + 0], g_conic[i * 3 + 1], g_conic[i * 3 + 2]};
+    float gS[9], gJ[6];
+    conic_bwd<float>(S9, J, W, gc, gS, gJ);
+    float gq[4], gs[3];
+    sigma_world_bwd<float>(qw, qx, qy, qz, s0, s1, s2, gS, gq, gs);
+    float gp_j[3], gp_uv[3] = {0.f, 0.f, 0.f};
+    proj_jacobian_bwd<float>(px, py, pz, vc.K[0], vc.K[4], gJ, gp_j);
+    project_uv_bwd<float>(px, py, pz, vc.K[0], vc.K[4], g_uv[i * 2 + 0], g_uv[i * 2 + 1], gp_uv);
+    const float gp[3] = {gp_j[0] + gp_uv[0], gp_j[1] + gp_uv[1], gp_j[2] + gp_uv[2]};
+    // xyz_cam = W xyz + t  =>  grad_xyz = W^T grad_xyz_cam
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o_xyz[i * 3 + k] = W[0 + k] * gp[0] + W[3 + k] * gp[1] + W[6 + k] * gp[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o_quat[i * 4 + k] = gq[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o_scale[i * 3 + k] = gs[k];
+    const float sg = sigmoid_torch(opa_logit[i]);
+    o_opa[i] = g_opa[i] * ((1.0f - sg) * sg);  // torch sigmoid_backward: grad * (1 - y) * y
+
+    const float gr[3] = {g_rgb[i * 3 + 0], g_rgb[i * 3 + 1], g_rgb[i * 3 + 2]};
+    if (HAS_SH) {
+        // src/precompute_sh.cu:96-109, split into the DC column and the rest
+        float dx, dy, dz, Y[N_SH];
+        view_dir<float>(x, y, z, vc.cam[0], vc.cam[1], vc.cam[2], dx, dy, dz);
+        sh_basis<float, N_SH>(dx, dy, dz, Y);
+        float* dst = o_sh + (size_t)i * 3 * NR;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float g = gr[c] * GSR_RSH0;
+            o_dc[i * 3 + c] = g * Y[0];
+#pragma unroll
+            for (int k = 1; k < N_SH; ++k) dst[c * NR + (k - 1)] = g * Y[k];
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o_dc[i * 3 + c] = gr[c];
+    }
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+size_t gsr_preprocess_temp_bytes(int N) {
+    size_t b = 0;
+    cub::DeviceScan::InclusiveSum((void*)nullptr, b, (uint64_t*)nullptr, (uint64_t*)nullptr, N > 0 ? N : 1);
+    return align256(b) + align256(sizeof(uint64_t) * (size_t)(N > 0 ? N : 1));
+}
+
+int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
+                           const float* scale, const float* opacity_logit, const float* rgb_dc,
+                           const float* sh_rest, const float* camera_T_world, const float* K, int H,
+                           int W, float near_thresh, float far_thresh, float cull_mask_padding,
+                           float mh_dist, float* records, uint32_t* depth_key, uint8_t* visible,
+                           uint64_t* scan, void* temp, size_t temp_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0) return GSR_OK;
+    if (temp_bytes < gsr_preprocess_temp_bytes(N)) return GSR_ERR_BAD_ARG;
+    size_t scan_bytes = 0;
+    cub::DeviceScan::InclusiveSum((void*)nullptr, scan_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, N);
+    uint64_t* packed = reinterpret_cast<uint64_t*>((char*)temp + align256(scan_bytes));
+    const int ntx = (W + TILE - 1) / TILE, nty = (H + TILE - 1) / TILE;
+    const dim3 grid((N + PRE_THREADS - 1) / PRE_THREADS), block(PRE_THREADS);
+#define GSR_PRE_ARGS                                                                              \
+    N, xyz, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K, (float)W, (float)H, \
+        near_thresh, far_thresh, cull_mask_padding, mh_dist, ntx, nty, records, depth_key, visible, packed
+    switch (n_sh_rest) {
+        case 0: k_preprocess_fwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
+        case 3: k_preprocess_fwd<4, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
+        case 8: k_preprocess_fwd<9, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
+        case 15: k_preprocess_fwd<16, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
+        default: return GSR_ERR_UNSUPPORTED;
+    }
+#undef GSR_PRE_ARGS
+    cudaError_t e = cub::DeviceScan::InclusiveSum(temp, scan_bytes, packed, scan, N, st);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+
+int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
+                            const float* scale, const float* opacity_logit, const float* camera_T_world,
+                            const float* K, const uint8_t* visible, const float* grad_rgb,
+                            const float* grad_opacity, const float* grad_uv, const float* grad_conic,
+                            float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
+                            float* g_rgb_dc, float* g_sh_rest, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0) return GSR_OK;
+    const dim3 grid((N + PRE_THREADS - 1) / PRE_THREADS), block(PRE_THREADS);
+#define GSR_PRE_ARGS                                                                                   \
+    N, xyz, quaternion, scale, opacity_logit, camera_T_world, K, visible, grad_rgb, grad_opacity, grad_uv, \
+        grad_conic, g_xyz, g_quaternion, g_scale, g_opacity_logit, g_rgb_dc, g_sh_rest
+    switch (n_sh_rest) {
+        case 0: k_preprocess_bwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
+        case 3: k_preprocess_bwd<4, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
+        case 8: k_preprocess_bwd<9, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
+        case 15: k_preprocess_bwd<16, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
+        default: return GSR_ERR_UNSUPPORTED;
+    }
+#undef GSR_PRE_ARGS
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,601 @@
+// splat_cuda_module.cpp — torch binding that re-exports the C ABI (include/gsr_b200.h) under the
+// reference's module surface: the 14 callables of src/bindings.cpp:118-159 with the same names,
+// argument order, in-place-output convention and error behaviour (TORCH_CHECK -> RuntimeError;
+// checks mirror src/checks.cuh:5-14 and the per-op shape checks), plus the fused entry points
+// used by gaussian_splatting_b200.rasterize.  Tensors are only unwrapped to raw pointers here;
+// all arithmetic is behind the C ABI.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <tuple>
+
+#include "../../include/gsr_b200.h"
+
+namespace {
+
+#define CHECK_VALID_INPUT(x)                                        \
+    TORCH_CHECK((x).is_cuda(), #x " is not a CUDA tensor");         \
+    TORCH_CHECK((x).is_contiguous(), #x " is not a contiguous tensor")
+#define CHECK_FLOAT_TENSOR(x) TORCH_CHECK((x).dtype() == torch::kFloat32, #x " is not a float tensor")
+#define CHECK_DOUBLE_TENSOR(x) TORCH_CHECK((x).dtype() == torch::kFloat64, #x " is not a double tensor")
+#define CHECK_INT_TENSOR(x) TORCH_CHECK((x).dtype() == torch::kInt32, #x " is not an int tensor")
+
+inline void* cur_stream() { return (void*)at::cuda::getCurrentCUDAStream().stream(); }
+
+inline void check_rc(int rc, const char* what) {
+    TORCH_CHECK(rc == 0, what, " failed with status ", rc,
+                rc > 0 ? std::string(" (") + cudaGetErrorString((cudaError_t)rc) + ")" : std::string());
+}
+
+// dtype of `lead`; every tensor in `rest` must match (reference: CHECK_FLOAT_TENSOR / CHECK_DOUBLE_TENSOR)
+inline int common_dtype(const torch::Tensor& lead, std::initializer_list<const torch::Tensor*> rest) {
+    if (lead.dtype() == torch::kFloat32) {
+        for (auto* t : rest) TORCH_CHECK(t->dtype() == torch::kFloat32, "tensor is not a float tensor");
+        return GSR_F32;
+    }
+    if (lead.dtype() == torch::kFloat64) {
+        for (auto* t : rest) TORCH_CHECK(t->dtype() == torch::kFloat64, "tensor is not a double tensor");
+        return GSR_F64;
+    }
+    AT_ERROR("Inputs must be float32 or float64");
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-Gaussian operators
+// ---------------------------------------------------------------------------------------------
+void camera_projection_cuda(torch::Tensor xyz, torch::Tensor K, torch::Tensor uv) {
+    CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(K); CHECK_VALID_INPUT(uv);
+    const int N = xyz.size(0);
+    TORCH_CHECK(xyz.size(1) == 3, "xyz must have shape Nx3");
+    TORCH_CHECK(K.size(0) == 3 && K.size(1) == 3, "K must have shape 3x3");
+    TORCH_CHECK(uv.size(0) == N && uv.size(1) == 2, "uv must have shape Nx2");
+    const int dt = common_dtype(xyz, {&K, &uv});
+    c10::cuda::CUDAGuard guard(xyz.device());
+    check_rc(gsr_camera_projection(dt, N, xyz.data_ptr(), K.data_ptr(), uv.data_ptr(), cur_stream()),
+             "camera_projection_cuda");
+}
+
+void camera_projection_backward_cuda(torch::Tensor xyz, torch::Tensor K, torch::Tensor uv_grad_out,
+                                     torch::Tensor xyz_grad_in) {
+    CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(K); CHECK_VALID_INPUT(uv_grad_out); CHECK_VALID_INPUT(xyz_grad_in);
+    const int N = xyz.size(0);
+    TORCH_CHECK(xyz.size(1) == 3, "xyz must be of shape Nx3");
+    TORCH_CHECK(K.size(0) == 3 && K.size(1) == 3, "K must be of shape 3x3");
+    TORCH_CHECK(uv_grad_out.size(0) == N && uv_grad_out.size(1) == 2, "uv_grad_out must be of shape Nx2");
+    TORCH_CHECK(xyz_grad_in.size(0) == N && xyz_grad_in.size(1) == 3, "xyz_grad_in must be of shape Nx3");
+    const int dt = common_dtype(xyz, {&K, &uv_grad_out, &xyz_grad_in});
+    c10::cuda::CUDAGuard guard(xyz.device());
+    check_rc(gsr_camera_projection_backward(dt, N, xyz.data_ptr(), K.data_ptr(), uv_grad_out.data_ptr(),
+                                            xyz_grad_in.data_ptr(), cur_stream()),
+             "camera_projection_backward_cuda");
+}
+
+void compute_sigma_world_cuda(torch::Tensor quaternion, torch::Tensor scale, torch::Tensor sigma_world) {
+    CHECK_VALID_INPUT(quaternion); CHECK_VALID_INPUT(scale); CHECK_VALID_INPUT(sigma_world);
+    const int N = quaternion.size(0);
+    TORCH_CHECK(quaternion.size(1) == 4, "quaternion must have shape Nx4");
+    TORCH_CHECK(scale.size(0) == N, "scale must have shape Nx3");
+    TORCH_CHECK(sigma_world.size(0) == N && sigma_world.size(1) == 3 && sigma_world.size(2) == 3,
+                "sigma_world must have shape Nx3x3");
+    const int dt = common_dtype(quaternion, {&scale, &sigma_world});
+    c10::cuda::CUDAGuard guard(quaternion.device());
+    check_rc(gsr_compute_sigma_world(dt, N, quaternion.data_ptr(), scale.data_ptr(), sigma_world.data_ptr(),
+                                     cur_stream()),
+             "compute_sigma_world_cuda");
+}
+
+void compute_sigma_world_backward_cuda(torch::Tensor quaternion, torch::Tensor scale,
+                                       torch::Tensor sigma_world_grad_out, torch::Tensor quaternion_grad_in,
+                                       torch::Tensor scale_grad_in) {
+    CHECK_VALID_INPUT(quaternion); CHECK_VALID_INPUT(scale); CHECK_VALID_INPUT(sigma_world_grad_out);
+    CHECK_VALID_INPUT(quaternion_grad_in); CHECK_VALID_INPUT(scale_grad_in);
+    const int N = quaternion.size(0);
+    TORCH_CHECK(quaternion.size(1) == 4, "quaternion must have shape Nx4");
+    TORCH_CHECK(scale.size(0) == N && scale.size(1) == 3, "scale must have shape Nx3");
+    TORCH_CHECK(sigma_world_grad_out.size(0) == N && sigma_world_grad_out.size(1) == 3 &&
+                    sigma_world_grad_out.size(2) == 3,
+                "sigma_world_grad_out must have shape Nx3x3");
+    TORCH_CHECK(quaternion_grad_in.size(0) == N && quaternion_grad_in.size(1) == 4,
+                "quaternion_grad_in must have shape Nx4");
+    TORCH_CHECK(scale_grad_in.size(0) == N && scale_grad_in.size(1) == 3, "scale_grad_in must have shape Nx3");
+    const int dt = common_dtype(quaternion, {&scale, &sigma_world_grad_out, &quaternion_grad_in, &scale_grad_in});
+    c10::cuda::CUDAGuard guard(quaternion.device());
+    check_rc(gsr_compute_sigma_world_backward(dt, N, quaternion.data_ptr(), scale.data_ptr(),
+                                              sigma_world_grad_out.data_ptr(), quaternion_grad_in.data_ptr(),
+                                              scale_grad_in.data_ptr(), cur_stream()),
+             "compute_sigma_world_backward_cuda");
+}
+
+void compute_projection_jacobian_cuda(torch::Tensor xyz, torch::Tensor K, torch::Tensor J) {
+    CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(K); CHECK_VALID_INPUT(J);
+    const int N = xyz.size(0);
+    TORCH_CHECK(xyz.size(1) == 3, "xyz must have shape Nx3");
+    TORCH_CHECK(K.size(0) == 3 && K.size(1) == 3, "K must have shape 3x3");
+    TORCH_CHECK(J.size(0) == N && J.size(1) == 2 && J.size(2) == 3, "J must have shape Nx2x3");
+    const int dt = common_dtype(xyz, {&K, &J});
+    c10::cuda::CUDAGuard guard(xyz.device());
+    check_rc(gsr_compute_projection_jacobian(dt, N, xyz.data_ptr(), K.data_ptr(), J.data_ptr(), cur_stream()),
+             "compute_projection_jacobian_cuda");
+}
+
+void compute_projection_jacobian_backward_cuda(torch::Tensor xyz, torch::Tensor K, torch::Tensor jac_grad_out,
+                                               torch::Tensor xyz_grad_in) {
+    CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(K); CHECK_VALID_INPUT(jac_grad_out); CHECK_VALID_INPUT(xyz_grad_in);
+    const int N = xyz.size(0);
+    TORCH_CHECK(xyz.size(1) == 3, "xyz must have shape Nx3");
+    TORCH_CHECK(K.size(0) == 3 && K.size(1) == 3, "K must have shape 3x3");
+    TORCH_CHECK(jac_grad_out.size(0) == N && jac_grad_out.size(1) == 2 && jac_grad_out.size(2) == 3,
+                "jac_grad_out must have shape Nx2x3");
+    TORCH_CHECK(xyz_grad_in.size(0) == N && xyz_grad_in.size(1) == 3, "xyz_grad_in must have shape Nx3");
+    const int dt = common_dtype(xyz, {&K, &jac_grad_out, &xyz_grad_in});
+    c10::cuda::CUDAGuard guard(xyz.device());
+    check_rc(gsr_compute_projection_jacobian_backward(dt, N, xyz.data_ptr(), K.data_ptr(),
+                                                      jac_grad_out.data_ptr(), xyz_grad_in.data_ptr(),
+                                                      cur_stream()),
+             "compute_projection_jacobian_backward_cuda");
+}
+
+void compute_conic_cuda(torch::Tensor sigma_world, torch::Tensor J, torch::Tensor camera_T_world,
+                        torch::Tensor conic) {
+    CHECK_VALID_INPUT(sigma_world); CHECK_VALID_INPUT(J); CHECK_VALID_INPUT(camera_T_world); CHECK_VALID_INPUT(conic);
+    const int N = sigma_world.size(0);
+    TORCH_CHECK(sigma_world.size(1) == 3 && sigma_world.size(2) == 3, "sigma_world must have shape Nx3x3");
+    TORCH_CHECK(J.size(0) == N && J.size(1) == 2 && J.size(2) == 3, "J must have shape Nx2x3");
+    TORCH_CHECK(camera_T_world.size(0) == 4 && camera_T_world.size(1) == 4, "camera_T_world must have shape 4x4");
+    TORCH_CHECK(conic.size(0) == N && conic.size(1) == 3, "conic must have shape Nx3");
+    const int dt = common_dtype(sigma_world, {&J, &camera_T_world, &conic});
+    c10::cuda::CUDAGuard guard(sigma_world.device());
+    check_rc(gsr_compute_conic(dt, N, sigma_world.data_ptr(), J.data_ptr(), camera_T_world.data_ptr(),
+                               conic.data_ptr(), cur_stream()),
+             "compute_conic_cuda");
+}
+
+void compute_conic_backward_cuda(torch::Tensor sigma_world, torch::Tensor J, torch::Tensor camera_T_world,
+                                 torch::Tensor conic_grad_out, torch::Tensor sigma_world_grad_in,
+                                 torch::Tensor J_grad_in) {
+    CHECK_VALID_INPUT(sigma_world); CHECK_VALID_INPUT(J); CHECK_VALID_INPUT(camera_T_world);
+    CHECK_VALID_INPUT(conic_grad_out); CHECK_VALID_INPUT(sigma_world_grad_in); CHECK_VALID_INPUT(J_grad_in);
+    const int N = sigma_world.size(0);
+    TORCH_CHECK(sigma_world.size(1) == 3 && sigma_world.size(2) == 3, "sigma_world must have shape Nx3x3");
+    TORCH_CHECK(J.size(0) == N && J.size(1) == 2 && J.size(2) == 3, "J must have shape Nx2x3");
+    TORCH_CHECK(camera_T_world.size(0) == 4 && camera_T_world.size(1) == 4, "camera_T_world must have shape 4x4");
+    TORCH_CHECK(conic_grad_out.size(0) == N && conic_grad_out.size(1) == 3, "conic_grad_out must have shape Nx3");
+    TORCH_CHECK(sigma_world_grad_in.size(0) == N && sigma_world_grad_in.size(1) == 3 &&
+                    sigma_world_grad_in.size(2) == 3,
+                "sigma_world_grad_in must have shape Nx3x3");
+    TORCH_CHECK(J_grad_in.size(0) == N && J_grad_in.size(1) == 2 && J_grad_in.size(2) == 3,
+                "J_grad_in must have shape Nx2x3");
+    const int dt =
+        common_dtype(sigma_world, {&J, &camera_T_world, &conic_grad_out, &sigma_world_grad_in, &J_grad_in});
+    c10::cuda::CUDAGuard guard(sigma_world.device());
+    check_rc(gsr_compute_conic_backward(dt, N, sigma_world.data_ptr(), J.data_ptr(), camera_T_world.data_ptr(),
+                                        conic_grad_out.data_ptr(), sigma_world_grad_in.data_ptr(),
+                                        J_grad_in.data_ptr(), cur_stream()),
+             "compute_conic_backward_cuda");
+}
+
+void precompute_rgb_from_sh_cuda(const torch::Tensor xyz, const torch::Tensor sh_coeff,
+                                 const torch::Tensor camera_T_world, torch::Tensor rgb) {
+    CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(sh_coeff); CHECK_VALID_INPUT(camera_T_world); CHECK_VALID_INPUT(rgb);
+    const int N = xyz.size(0);
+    TORCH_CHECK(xyz.size(1) == 3, "Input xyz should have 3 channels");
+    TORCH_CHECK(sh_coeff.size(0) == N, "N xyz and sh_coeff should match");
+    TORCH_CHECK(sh_coeff.size(1) == 3, "SH coefficients should have 3 channels");
+    const int n_sh = sh_coeff.dim() == 3 ? (int)sh_coeff.size(2) : 1;
+    TORCH_CHECK(camera_T_world.size(0) == 4 && camera_T_world.size(1) == 4,
+                "camera_T_world should be 4x4 transformation matrix");
+    TORCH_CHECK(rgb.size(0) == N && rgb.size(1) == 3, "Output rgb should be Nx3");
+    TORCH_CHECK(n_sh == 1 || n_sh == 4 || n_sh == 9 || n_sh == 16, "Invalid number of SH coefficients");
+    const int dt = common_dtype(xyz, {&sh_coeff, &camera_T_world, &rgb});
+    c10::cuda::CUDAGuard guard(xyz.device());
+    check_rc(gsr_precompute_rgb_from_sh(dt, N, n_sh, xyz.data_ptr(), sh_coeff.data_ptr(),
+                                        camera_T_world.data_ptr(), rgb.data_ptr(), cur_stream()),
+             "precompute_rgb_from_sh_cuda");
+}
+
+void precompute_rgb_from_sh_backward_cuda(const torch::Tensor xyz, const torch::Tensor camera_T_world,
+                                          const torch::Tensor grad_rgb, torch::Tensor grad_sh) {
+    CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(camera_T_world); CHECK_VALID_INPUT(grad_rgb); CHECK_VALID_INPUT(grad_sh);
+    const int N = xyz.size(0);
+    TORCH_CHECK(xyz.size(1) == 3, "Input xyz should have 3 channels");
+    TORCH_CHECK(camera_T_world.size(0) == 4 && camera_T_world.size(1) == 4,
+                "camera_T_world should be 4x4 transformation matrix");
+    TORCH_CHECK(grad_rgb.size(0) == N && grad_rgb.size(1) == 3, "grad_rgb should be Nx3");
+    TORCH_CHECK(grad_sh.size(0) == N && grad_sh.size(1) == 3, "grad_sh should be Nx3(xK)");
+    const int n_sh = grad_sh.dim() == 3 ? (int)grad_sh.size(2) : 1;
+    TORCH_CHECK(n_sh == 1 || n_sh == 4 || n_sh == 9 || n_sh == 16, "Invalid number of SH coefficients");
+    const int dt = common_dtype(xyz, {&camera_T_world, &grad_rgb, &grad_sh});
+    c10::cuda::CUDAGuard guard(xyz.device());
+    check_rc(gsr_precompute_rgb_from_sh_backward(dt, N, n_sh, xyz.data_ptr(), camera_T_world.data_ptr(),
+                                                 grad_rgb.data_ptr(), grad_sh.data_ptr(), cur_stream()),
+             "precompute_rgb_from_sh_backward_cuda");
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile binning
+// ---------------------------------------------------------------------------------------------
+std::tuple<torch::Tensor, torch::Tensor> get_sorted_gaussian_list(const int max_tiles_per_gaussian,
+                                                                  torch::Tensor uvs,
+                                                                  torch::Tensor xyz_camera_frame,
+                                                                  torch::Tensor conic, const int n_tiles_x,
+                                                                  const int n_tiles_y, const float mh_dist) {
+    (void)max_tiles_per_gaussian;  // ignored by the reference as well
+    CHECK_VALID_INPUT(uvs); CHECK_VALID_INPUT(xyz_camera_frame); CHECK_VALID_INPUT(conic);
+    CHECK_FLOAT_TENSOR(uvs); CHECK_FLOAT_TENSOR(xyz_camera_frame); CHECK_FLOAT_TENSOR(conic);
+    const int N = uvs.size(0);
+    TORCH_CHECK(xyz_camera_frame.size(0) == N && conic.size(0) == N, "uvs, xyz_camera_frame, conic must have N rows");
+    c10::cuda::CUDAGuard guard(uvs.device());
+    auto i32 = torch::dtype(torch::kInt32).device(uvs.device());
+    auto u8 = torch::dtype(torch::kUInt8).device(uvs.device());
+    torch::Tensor offsets = torch::empty({N + 1}, i32);
+    const size_t tb = gsr_binning_count_temp_bytes(N);
+    torch::Tensor temp = torch::empty({(int64_t)tb}, u8);
+    check_rc(gsr_binning_count(N, uvs.data_ptr<float>(), conic.data_ptr<float>(), n_tiles_x, n_tiles_y, mh_dist,
+                               offsets.data_ptr<int>(), temp.data_ptr(), tb, cur_stream()),
+             "gsr_binning_count");
+    const int P = offsets[N].item<int>();  // the one host sync of this operator (reference: three)
+    torch::Tensor sorted = torch::empty({P}, i32);
+    torch::Tensor ranges = torch::empty({n_tiles_x * n_tiles_y + 1}, i32);
+    const size_t sb = gsr_binning_sort_temp_bytes(P);
+    torch::Tensor temp2 = torch::empty({(int64_t)sb}, u8);
+    check_rc(gsr_binning_emit_sort(N, P, uvs.data_ptr<float>(), xyz_camera_frame.data_ptr<float>(),
+                                   conic.data_ptr<float>(), n_tiles_x, n_tiles_y, mh_dist,
+                                   offsets.data_ptr<int>(), sorted.data_ptr<int>(), ranges.data_ptr<int>(),
+                                   temp2.data_ptr(), sb, cur_stream()),
+             "gsr_binning_emit_sort");
+    return std::make_tuple(sorted, ranges);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile renderers
+// ---------------------------------------------------------------------------------------------
+struct RenderShapes {
+    int N, H, W, n_sh;
+};
+
+RenderShapes check_render_inputs(const torch::Tensor& uvs, const torch::Tensor& opacity, const torch::Tensor& rgb,
+                                 const torch::Tensor& conic, const torch::Tensor& view_dir_by_pixel,
+                                 const torch::Tensor& ranges, const torch::Tensor& idx,
+                                 const torch::Tensor& background_rgb, const torch::Tensor& image_like) {
+    RenderShapes s;
+    s.N = uvs.size(0);
+    TORCH_CHECK(uvs.size(1) == 2, "uvs must be Nx2 (u, v)");
+    TORCH_CHECK(opacity.size(0) == s.N, "Opacity must have the same number of elements as uvs");
+    TORCH_CHECK(opacity.size(1) == 1, "Opacity must be Nx1");
+    TORCH_CHECK(rgb.size(0) == s.N, "RGB must have the same number of elements as uvs");
+    TORCH_CHECK(rgb.size(1) == 3, "RGB must be Nx3");
+    TORCH_CHECK(conic.size(0) == s.N, "Conic must have the same number of elements as uvs");
+    TORCH_CHECK(conic.size(1) == 3, "Conic must be Nx3");
+    TORCH_CHECK(image_like.size(2) == 3, "Image must be HxWx3");
+    TORCH_CHECK(background_rgb.dim() == 1, "Background RGB must be 1D");
+    TORCH_CHECK(background_rgb.size(0) == 3, "Background RGB must have 3 elements");
+    s.H = image_like.size(0);
+    s.W = image_like.size(1);
+    s.n_sh = rgb.dim() == 3 ? (int)rgb.size(2) : 1;
+    TORCH_CHECK(s.n_sh == 1 || s.n_sh == 4 || s.n_sh == 9 || s.n_sh == 16, "Invalid number of SH coefficients");
+    if (s.n_sh > 1) {
+        TORCH_CHECK(view_dir_by_pixel.size(0) == s.H && view_dir_by_pixel.size(1) == s.W,
+                    "view_dir_by_pixel must have the same size as the image");
+        TORCH_CHECK(view_dir_by_pixel.size(2) == 3, "view_dir_by_pixel must have 3 channels");
+    }
+    CHECK_INT_TENSOR(ranges);
+    CHECK_INT_TENSOR(idx);
+    const int n_tiles = ((s.W + 15) / 16) * ((s.H + 15) / 16);
+    TORCH_CHECK(ranges.numel() == n_tiles + 1, "splat_start_end_idx_by_tile_idx must have n_tiles + 1 entries");
+    return s;
+}
+
+void render_tiles_cuda(torch::Tensor uvs, torch::Tensor opacity, torch::Tensor rgb, torch::Tensor conic,
+                       torch::Tensor view_dir_by_pixel, torch::Tensor splat_start_end_idx_by_tile_idx,
+                       torch::Tensor gaussian_idx_by_splat_idx, torch::Tensor background_rgb,
+                       torch::Tensor num_splats_per_pixel, torch::Tensor final_weight_per_pixel,
+                       torch::Tensor rendered_image) {
+    CHECK_VALID_INPUT(uvs); CHECK_VALID_INPUT(opacity); CHECK_VALID_INPUT(rgb); CHECK_VALID_INPUT(conic);
+    CHECK_VALID_INPUT(view_dir_by_pixel); CHECK_VALID_INPUT(splat_start_end_idx_by_tile_idx);
+    CHECK_VALID_INPUT(gaussian_idx_by_splat_idx); CHECK_VALID_INPUT(background_rgb);
+    CHECK_VALID_INPUT(num_splats_per_pixel); CHECK_VALID_INPUT(final_weight_per_pixel);
+    CHECK_VALID_INPUT(rendered_image);
+    const RenderShapes s = check_render_inputs(uvs, opacity, rgb, conic, view_dir_by_pixel,
+                                               splat_start_end_idx_by_tile_idx, gaussian_idx_by_splat_idx,
+                                               background_rgb, rendered_image);
+    CHECK_INT_TENSOR(num_splats_per_pixel);
+    const int dt = common_dtype(uvs, {&opacity, &rgb, &conic, &view_dir_by_pixel, &background_rgb,
+                                      &final_weight_per_pixel, &rendered_image});
+    c10::cuda::CUDAGuard guard(uvs.device());
+    const int P = gaussian_idx_by_splat_idx.numel();
+    if (dt == GSR_F32 && s.n_sh == 1) {
+        torch::Tensor records = torch::empty({std::max(P, 1), GSR_REC_FLOATS}, uvs.options());
+        check_rc(gsr_pack_records(P, gaussian_idx_by_splat_idx.data_ptr<int>(), uvs.data_ptr<float>(),
+                                  opacity.data_ptr<float>(), rgb.data_ptr<float>(), conic.data_ptr<float>(),
+                                  records.data_ptr<float>(), cur_stream()),
+                 "gsr_pack_records");
+        check_rc(gsr_render_forward(records.data_ptr<float>(), splat_start_end_idx_by_tile_idx.data_ptr<int>(),
+                                    background_rgb.data_ptr<float>(), s.H, s.W,
+                                    num_splats_per_pixel.data_ptr<int>(), final_weight_per_pixel.data_ptr<float>(),
+                                    rendered_image.data_ptr<float>(), cur_stream()),
+                 "gsr_render_forward");
+    } else {
+        check_rc(gsr_render_forward_generic(
+                     dt, s.N, s.n_sh, uvs.data_ptr(), opacity.data_ptr(), rgb.data_ptr(), conic.data_ptr(),
+                     view_dir_by_pixel.data_ptr(), splat_start_end_idx_by_tile_idx.data_ptr<int>(),
+                     gaussian_idx_by_splat_idx.data_ptr<int>(), background_rgb.data_ptr(), s.H, s.W,
+                     num_splats_per_pixel.data_ptr<int>(), final_weight_per_pixel.data_ptr(),
+                     rendered_image.data_ptr(), cur_stream()),
+                 "gsr_render_forward_generic");
+    }
+}
+
+void render_tiles_backward_cuda(torch::Tensor uvs, torch::Tensor opacity, torch::Tensor rgb, torch::Tensor conic,
+                                torch::Tensor view_dir_by_pixel, torch::Tensor splat_start_end_idx_by_tile_idx,
+                                torch::Tensor gaussian_idx_by_splat_idx, torch::Tensor background_rgb,
+                                torch::Tensor num_splats_per_pixel, torch::Tensor final_weight_per_pixel,
+                                torch::Tensor grad_image, torch::Tensor grad_rgb, torch::Tensor grad_opacity,
+                                torch::Tensor grad_uvs, torch::Tensor grad_conic) {
+    CHECK_VALID_INPUT(uvs); CHECK_VALID_INPUT(opacity); CHECK_VALID_INPUT(rgb); CHECK_VALID_INPUT(conic);
+    CHECK_VALID_INPUT(view_dir_by_pixel); CHECK_VALID_INPUT(splat_start_end_idx_by_tile_idx);
+    CHECK_VALID_INPUT(gaussian_idx_by_splat_idx); CHECK_VALID_INPUT(background_rgb);
+    CHECK_VALID_INPUT(num_splats_per_pixel); CHECK_VALID_INPUT(final_weight_per_pixel);
+    CHECK_VALID_INPUT(grad_image); CHECK_VALID_INPUT(grad_rgb); CHECK_VALID_INPUT(grad_opacity);
+    CHECK_VALID_INPUT(grad_uvs); CHECK_VALID_INPUT(grad_conic);
+    const RenderShapes s = check_render_inputs(uvs, opacity, rgb, conic, view_dir_by_pixel,
+                                               splat_start_end_idx_by_tile_idx, gaussian_idx_by_splat_idx,
+                                               background_rgb, grad_image);
+    CHECK_INT_TENSOR(num_splats_per_pixel);
+    TORCH_CHECK(grad_rgb.sizes() == rgb.sizes(), "grad_rgb must have the shape of rgb");
+    TORCH_CHECK(grad_opacity.size(0) == s.N, "grad_opacity must be Nx1");
+    TORCH_CHECK(grad_uvs.size(0) == s.N && grad_uvs.size(1) == 2, "grad_uvs must be Nx2");
+    TORCH_CHECK(grad_conic.size(0) == s.N && grad_conic.size(1) == 3, "grad_conic must be Nx3");
+    const int dt = common_dtype(uvs, {&opacity, &rgb, &conic, &view_dir_by_pixel, &background_rgb,
+                                      &final_weight_per_pixel, &grad_image, &grad_rgb, &grad_opacity, &grad_uvs,
+                                      &grad_conic});
+    c10::cuda::CUDAGuard guard(uvs.device());
+    const int P = gaussian_idx_by_splat_idx.numel();
+    if (dt == GSR_F32 && s.n_sh == 1) {
+        torch::Tensor records = torch::empty({std::max(P, 1), GSR_REC_FLOATS}, uvs.options());
+        check_rc(gsr_pack_records(P, gaussian_idx_by_splat_idx.data_ptr<int>(), uvs.data_ptr<float>(),
+                                  opacity.data_ptr<float>(), rgb.data_ptr<float>(), conic.data_ptr<float>(),
+                                  records.data_ptr<float>(), cur_stream()),
+                 "gsr_pack_records");
+        check_rc(gsr_render_backward(records.data_ptr<float>(), gaussian_idx_by_splat_idx.data_ptr<int>(),
+                                     splat_start_end_idx_by_tile_idx.data_ptr<int>(),
+                                     background_rgb.data_ptr<float>(), s.H, s.W,
+                                     num_splats_per_pixel.data_ptr<int>(), final_weight_per_pixel.data_ptr<float>(),
+                                     grad_image.data_ptr<float>(), grad_rgb.data_ptr<float>(),
+                                     grad_opacity.data_ptr<float>(), grad_uvs.data_ptr<float>(),
+                                     grad_conic.data_ptr<float>(), cur_stream()),
+                 "gsr_render_backward");
+    } else {
+        check_rc(gsr_render_backward_generic(
+                     dt, s.N, s.n_sh, uvs.data_ptr(), opacity.data_ptr(), rgb.data_ptr(), conic.data_ptr(),
+                     view_dir_by_pixel.data_ptr(), splat_start_end_idx_by_tile_idx.data_ptr<int>(),
+                     gaussian_idx_by_splat_idx.data_ptr<int>(), background_rgb.data_ptr(), s.H, s.W,
+                     num_splats_per_pixel.data_ptr<int>(), final_weight_per_pixel.data_ptr(),
+                     grad_image.data_ptr(), grad_rgb.data_ptr(), grad_opacity.data_ptr(), grad_uvs.data_ptr(),
+                     grad_conic.data_ptr(), cur_stream()),
+                 "gsr_render_backward_generic");
+    }
+}
+
+void render_depth_cuda(torch::Tensor xyz_camera_frame, torch::Tensor uvs, torch::Tensor opacity,
+                       torch::Tensor conic, torch::Tensor splat_start_end_idx_by_tile_idx,
+                       torch::Tensor gaussian_idx_by_splat_idx, const float alpha_threshold,
+                       torch::Tensor depth_image) {
+    CHECK_VALID_INPUT(xyz_camera_frame); CHECK_VALID_INPUT(uvs); CHECK_VALID_INPUT(opacity); CHECK_VALID_INPUT(conic);
+    CHECK_VALID_INPUT(splat_start_end_idx_by_tile_idx); CHECK_VALID_INPUT(gaussian_idx_by_splat_idx);
+    CHECK_VALID_INPUT(depth_image);
+    CHECK_FLOAT_TENSOR(xyz_camera_frame); CHECK_FLOAT_TENSOR(uvs); CHECK_FLOAT_TENSOR(opacity);
+    CHECK_FLOAT_TENSOR(conic); CHECK_FLOAT_TENSOR(depth_image);
+    CHECK_INT_TENSOR(splat_start_end_idx_by_tile_idx); CHECK_INT_TENSOR(gaussian_idx_by_splat_idx);
+    const int N = uvs.size(0);
+    TORCH_CHECK(uvs.size(1) == 2, "uvs must be Nx2 (u, v)");
+    TORCH_CHECK(xyz_camera_frame.size(0) == N && xyz_camera_frame.size(1) == 3, "xyz_camera_frame must be Nx3");
+    TORCH_CHECK(opacity.size(0) == N, "Opacity must have the same number of elements as uvs");
+    TORCH_CHECK(conic.size(0) == N && conic.size(1) == 3, "Conic must be Nx3");
+    const int H = depth_image.size(0), W = depth_image.size(1);
+    c10::cuda::CUDAGuard guard(uvs.device());
+    check_rc(gsr_render_depth(N, xyz_camera_frame.data_ptr<float>(), uvs.data_ptr<float>(),
+                              opacity.data_ptr<float>(), conic.data_ptr<float>(),
+                              splat_start_end_idx_by_tile_idx.data_ptr<int>(),
+                              gaussian_idx_by_splat_idx.data_ptr<int>(), alpha_threshold, H, W,
+                              depth_image.data_ptr<float>(), cur_stream()),
+             "render_depth_cuda");
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused path (used by gaussian_splatting_b200.rasterize): thin pointer plumbing, no arithmetic
+// ---------------------------------------------------------------------------------------------
+#define F32PTR(t) ((t).data_ptr<float>())
+
+// returns (records[N,12], depth_key[N] i32-viewed u32, visible[N] u8, scan[N] i64-viewed u64)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_preprocess_forward(
+    torch::Tensor xyz, torch::Tensor quaternion, torch::Tensor scale, torch::Tensor opacity_logit,
+    torch::Tensor rgb_dc, c10::optional<torch::Tensor> sh_rest, torch::Tensor camera_T_world, torch::Tensor K,
+    int64_t H, int64_t W, double near_thresh, double far_thresh, double cull_mask_padding, double mh_dist) {
+    CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(quaternion); CHECK_VALID_INPUT(scale); CHECK_VALID_INPUT(opacity_logit);
+    CHECK_VALID_INPUT(rgb_dc); CHECK_VALID_INPUT(camera_T_world); CHECK_VALID_INPUT(K);
+    CHECK_FLOAT_TENSOR(xyz); CHECK_FLOAT_TENSOR(quaternion); CHECK_FLOAT_TENSOR(scale);
+    CHECK_FLOAT_TENSOR(opacity_logit); CHECK_FLOAT_TENSOR(rgb_dc); CHECK_FLOAT_TENSOR(camera_T_world);
+    CHECK_FLOAT_TENSOR(K);
+    const int N = xyz.size(0);
+    TORCH_CHECK(xyz.dim() == 2 && xyz.size(1) == 3, "xyz must have shape Nx3");
+    TORCH_CHECK(quaternion.size(0) == N && quaternion.size(1) == 4, "quaternion must have shape Nx4");
+    TORCH_CHECK(scale.size(0) == N && scale.size(1) == 3, "scale must have shape Nx3");
+    TORCH_CHECK(opacity_logit.numel() == N, "opacity must have shape Nx1");
+    TORCH_CHECK(rgb_dc.size(0) == N && rgb_dc.size(1) == 3, "rgb must have shape Nx3");
+    TORCH_CHECK(camera_T_world.numel() == 16 && K.numel() == 9, "camera_T_world must be 4x4 and K 3x3");
+    int n_rest = 0;
+    const float* sh_ptr = nullptr;
+    if (sh_rest.has_value()) {
+        const torch::Tensor& sh = *sh_rest;
+        CHECK_VALID_INPUT(sh); CHECK_FLOAT_TENSOR(sh);
+        TORCH_CHECK(sh.dim() == 3 && sh.size(0) == N && sh.size(1) == 3, "sh must have shape Nx3xK");
+        n_rest = sh.size(2);
+        TORCH_CHECK(n_rest == 3 || n_rest == 8 || n_rest == 15, "sh must hold 3, 8 or 15 coefficients per channel");
+        sh_ptr = sh.data_ptr<float>();
+    }
+    c10::cuda::CUDAGuard guard(xyz.device());
+    auto opt = xyz.options();
+    torch::Tensor records = torch::empty({N, GSR_REC_FLOATS}, opt);
+    torch::Tensor zkey = torch::empty({N}, opt.dtype(torch::kInt32));
+    torch::Tensor visible = torch::empty({N}, opt.dtype(torch::kUInt8));
+    torch::Tensor scan = torch::empty({N}, opt.dtype(torch::kInt64));
+    const size_t tb = gsr_preprocess_temp_bytes(N);
+    torch::Tensor temp = torch::empty({(int64_t)tb}, opt.dtype(torch::kUInt8));
+    check_rc(gsr_preprocess_forward(N, n_rest, F32PTR(xyz), F32PTR(quaternion), F32PTR(scale),
+                                    F32PTR(opacity_logit), F32PTR(rgb_dc), sh_ptr, F32PTR(camera_T_world),
+                                    F32PTR(K), (int)H, (int)W, (float)near_thresh, (float)far_thresh,
+                                    (float)cull_mask_padding, (float)mh_dist, F32PTR(records),
+                                    (uint32_t*)zkey.data_ptr<int>(), visible.data_ptr<uint8_t>(),
+                                    (uint64_t*)scan.data_ptr<int64_t>(), temp.data_ptr(), tb, cur_stream()),
+             "gsr_preprocess_forward");
+    return std::make_tuple(records, zkey, visible, scan);
+}
+
+// (M, P known) -> sorted ids [P] i32, tile ranges [n_tiles+1] i32, sorted record stream [P,12],
+//                 vis_idx [M] i32, uv [M,2]
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_bin(
+    torch::Tensor records, torch::Tensor zkey, torch::Tensor visible, torch::Tensor scan, int64_t M, int64_t P,
+    int64_t H, int64_t W, double mh_dist) {
+    const int N = records.size(0);
+    const int ntx = (W + 15) / 16, nty = (H + 15) / 16, n_tiles = ntx * nty;
+    c10::cuda::CUDAGuard guard(records.device());
+    auto opt = records.options();
+    auto i32 = opt.dtype(torch::kInt32);
+    const int64_t Pa = std::max<int64_t>(P, 1);
+    torch::Tensor keys = torch::empty({2 * Pa}, opt.dtype(torch::kInt64));
+    torch::Tensor ids = torch::empty({Pa}, i32);
+    torch::Tensor ids_sorted = torch::empty({Pa}, i32);
+    torch::Tensor vis_idx = torch::empty({M}, i32);
+    torch::Tensor uv = torch::empty({M, 2}, opt);
+    torch::Tensor ranges = torch::empty({n_tiles + 1}, i32);
+    torch::Tensor stream_rec = torch::empty({Pa, GSR_REC_FLOATS}, opt);
+    uint64_t* keys_a = (uint64_t*)keys.data_ptr<int64_t>();
+    uint64_t* keys_b = keys_a + Pa;
+    check_rc(gsr_emit_pairs(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(),
+                            visible.data_ptr<uint8_t>(), (const uint64_t*)scan.data_ptr<int64_t>(), ntx, nty,
+                            (float)mh_dist, keys_a, (uint32_t*)ids.data_ptr<int>(), vis_idx.data_ptr<int>(),
+                            F32PTR(uv), cur_stream()),
+             "gsr_emit_pairs");
+    const size_t sb = gsr_sort_pairs_temp_bytes((int)P);
+    torch::Tensor temp = torch::empty({(int64_t)sb}, opt.dtype(torch::kUInt8));
+    check_rc(gsr_sort_pairs((int)P, n_tiles, keys_a, (const uint32_t*)ids.data_ptr<int>(), keys_b,
+                            (uint32_t*)ids_sorted.data_ptr<int>(), temp.data_ptr(), sb, cur_stream()),
+             "gsr_sort_pairs");
+    check_rc(gsr_tile_ranges((int)P, n_tiles, keys_b, ranges.data_ptr<int>(), cur_stream()), "gsr_tile_ranges");
+    check_rc(gsr_gather_records((int)P, (const uint32_t*)ids_sorted.data_ptr<int>(), F32PTR(records),
+                                F32PTR(stream_rec), cur_stream()),
+             "gsr_gather_records");
+    return std::make_tuple(ids_sorted.narrow(0, 0, P), ranges, stream_rec, vis_idx, uv);
+}
+
+// image [H,W,3], n [H,W] i32, wlast [H,W]
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> fused_render_forward(torch::Tensor stream_rec,
+                                                                             torch::Tensor ranges,
+                                                                             torch::Tensor background, int64_t H,
+                                                                             int64_t W) {
+    CHECK_VALID_INPUT(background); CHECK_FLOAT_TENSOR(background);
+    TORCH_CHECK(background.numel() == 3, "Background RGB must have 3 elements");
+    c10::cuda::CUDAGuard guard(stream_rec.device());
+    auto opt = stream_rec.options();
+    torch::Tensor image = torch::empty({H, W, 3}, opt);
+    torch::Tensor n = torch::empty({H, W}, opt.dtype(torch::kInt32));
+    torch::Tensor w = torch::empty({H, W}, opt);
+    check_rc(gsr_render_forward(F32PTR(stream_rec), ranges.data_ptr<int>(), F32PTR(background), (int)H, (int)W,
+                                n.data_ptr<int>(), F32PTR(w), F32PTR(image), cur_stream()),
+             "gsr_render_forward");
+    return std::make_tuple(image, n, w);
+}
+
+// per-gaussian gradient slab, flat [9N]: rgb [N,3] | opacity [N] | uv [N,2] | conic [N,3], rows indexed
+// by ORIGINAL gaussian index; zero-filled, then accumulated into by the render backward
+torch::Tensor fused_render_backward(torch::Tensor grad_image, int64_t N, torch::Tensor stream_rec,
+                                    torch::Tensor ids_sorted, torch::Tensor ranges, torch::Tensor background,
+                                    torch::Tensor n, torch::Tensor w) {
+    CHECK_VALID_INPUT(grad_image); CHECK_FLOAT_TENSOR(grad_image);
+    const int H = n.size(0), W = n.size(1);
+    TORCH_CHECK(grad_image.dim() == 3 && grad_image.size(0) == H && grad_image.size(1) == W &&
+                    grad_image.size(2) == 3,
+                "grad_image must be HxWx3");
+    c10::cuda::CUDAGuard guard(grad_image.device());
+    torch::Tensor slab = torch::zeros({N * 9}, grad_image.options());
+    float* g_rgb = slab.data_ptr<float>();
+    float* g_opa = g_rgb + (size_t)N * 3;
+    float* g_uv = g_opa + (size_t)N;
+    float* g_conic = g_uv + (size_t)N * 2;
+    check_rc(gsr_render_backward(F32PTR(stream_rec), ids_sorted.data_ptr<int>(), ranges.data_ptr<int>(),
+                                 F32PTR(background), H, W, n.data_ptr<int>(), F32PTR(w), F32PTR(grad_image),
+                                 g_rgb, g_opa, g_uv, g_conic, cur_stream()),
+             "gsr_render_backward");
+    return slab;
+}
+
+// grads of (xyz, quaternion, scale, opacity_logit, rgb_dc[, sh_rest]) from the slab
+std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::Tensor xyz,
+                                                     torch::Tensor quaternion, torch::Tensor scale,
+                                                     torch::Tensor opacity_logit,
+                                                     c10::optional<torch::Tensor> sh_rest,
+                                                     torch::Tensor camera_T_world, torch::Tensor K,
+                                                     torch::Tensor visible) {
+    CHECK_VALID_INPUT(slab); CHECK_FLOAT_TENSOR(slab);
+    const int64_t N = xyz.size(0);
+    TORCH_CHECK(slab.numel() == N * 9, "gradient slab must hold 9 floats per gaussian");
+    c10::cuda::CUDAGuard guard(xyz.device());
+    auto opt = xyz.options();
+    const float* g_rgb = slab.data_ptr<float>();
+    const float* g_opa = g_rgb + (size_t)N * 3;
+    const float* g_uv = g_opa + (size_t)N;
+    const float* g_conic = g_uv + (size_t)N * 2;
+    int n_rest = 0;
+    torch::Tensor g_sh;
+    if (sh_rest.has_value()) {
+        n_rest = sh_rest->size(2);
+        g_sh = torch::empty_like(*sh_rest);
+    }
+    torch::Tensor o_xyz = torch::empty_like(xyz), o_q = torch::empty_like(quaternion),
+                  o_s = torch::empty_like(scale), o_o = torch::empty_like(opacity_logit),
+                  o_dc = torch::empty({N, 3}, opt);
+    check_rc(gsr_preprocess_backward((int)N, n_rest, F32PTR(xyz), F32PTR(quaternion), F32PTR(scale),
+                                     F32PTR(opacity_logit), F32PTR(camera_T_world), F32PTR(K),
+                                     visible.data_ptr<uint8_t>(), g_rgb, g_opa, g_uv, g_conic, F32PTR(o_xyz),
+                                     F32PTR(o_q), F32PTR(o_s), F32PTR(o_o), F32PTR(o_dc),
+                                     n_rest ? F32PTR(g_sh) : nullptr, cur_stream()),
+             "gsr_preprocess_backward");
+    std::vector<torch::Tensor> out = {o_xyz, o_q, o_s, o_o, o_dc};
+    if (n_rest) out.push_back(g_sh);
+    return out;
+}
+
+std::string version() { return gsr_version(); }
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    // the reference surface (src/bindings.cpp:118-159)
+    m.def("render_tiles_cuda", &render_tiles_cuda, "Render tiles CUDA");
+    m.def("render_tiles_backward_cuda", &render_tiles_backward_cuda, "Render tiles backward");
+    m.def("camera_projection_cuda", &camera_projection_cuda, "project point into image CUDA");
+    m.def("camera_projection_backward_cuda", &camera_projection_backward_cuda,
+          "project point into image backward CUDA");
+    m.def("compute_sigma_world_cuda", &compute_sigma_world_cuda, "compute sigma world CUDA");
+    m.def("compute_sigma_world_backward_cuda", &compute_sigma_world_backward_cuda,
+          "compute sigma world backward CUDA");
+    m.def("compute_projection_jacobian_cuda", &compute_projection_jacobian_cuda,
+          "compute projection jacobian CUDA");
+    m.def("compute_projection_jacobian_backward_cuda", &compute_projection_jacobian_backward_cuda,
+          "compute projection jacobian backward CUDA");
+    m.def("compute_conic_cuda", &compute_conic_cuda, "compute conic CUDA");
+    m.def("compute_conic_backward_cuda", &compute_conic_backward_cuda, "compute conic backward CUDA");
+    m.def("get_sorted_gaussian_list", &get_sorted_gaussian_list, "get sorted gaussian list");
+    m.def("precompute_rgb_from_sh_cuda", &precompute_rgb_from_sh_cuda, "precompute rgb from sh per gaussian");
+    m.def("precompute_rgb_from_sh_backward_cuda", &precompute_rgb_from_sh_backward_cuda,
+          "precompute rgb from sh per gaussian backward");
+    m.def("render_depth_cuda", &render_depth_cuda, "Render depth CUDA");
+    // fused path
+    m.def("fused_preprocess_forward", &fused_preprocess_forward, "fused per-gaussian stage");
+    m.def("fused_bin", &fused_bin, "pair emission + radix sort + tile ranges + record stream");
+    m.def("fused_render_forward", &fused_render_forward, "tile renderer forward on a record stream");
+    m.def("fused_render_backward", &fused_render_backward, "tile renderer backward -> per-gaussian gradient slab");
+    m.def("fused_preprocess_backward", &fused_preprocess_backward, "fused per-gaussian backward");
+    m.def("version", &version, "library version string");
+}

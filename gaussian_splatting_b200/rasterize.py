@@ -1,0 +1,163 @@
+"""rasterize(): drop-in for splat_py.rasterize.rasterize (splat_py/rasterize.py:18-112).
+
+Same nine positional arguments, same return triple ``(image [H,W,3], culling_mask [N] bool,
+uv [M,2])``, same values.  ``uv`` is a graph tensor whose ``.grad`` after ``backward()`` is the
+render pass's gradient on the projected means, exactly what the reference trainer reads for
+densification (splat_py/trainer.py:360,379-385).
+
+Implementation: two autograd nodes around the native fused kernels
+
+    _ProjectGaussians   params -> uv [M,2], carrier          (gsr_preprocess_forward + binning)
+    _CompositeTiles     uv, carrier -> image                  (gsr_render_forward)
+
+``carrier`` is an uninitialised [9N] tensor that only carries gradient: the render backward
+returns its per-Gaussian sums (rgb, opacity, uv, conic) as the carrier's gradient, and the
+per-Gaussian backward consumes them.  One host sync per forward (to size the pair buffers);
+the reference path has ~25.
+
+``use_sh_precompute=False`` (per-pixel view directions) is routed through the operator-by-operator
+path `rasterize_unfused`, which mirrors the reference's structure on this library's operators.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import native
+from .cuda_autograd_functions import (
+    CameraPointProjection,
+    ComputeConic,
+    ComputeProjectionJacobian,
+    ComputeSigmaWorld,
+    PrecomputeRGBFromSH,
+    RenderImage,
+)
+from .structs import Tiles
+from .tile_culling import get_splats
+from .utils import compute_rays_in_world_frame, transform_points_torch
+
+
+class _ViewState:
+    """Non-differentiable per-view buffers shared by the two autograd nodes."""
+
+    __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
+                 "n_per_pixel", "w_per_pixel", "background", "stats")
+
+
+class _ProjectGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, quaternion, scale, opacity, rgb, sh, camera_T_world, K, state, cfg):
+        ext = native()
+        H, W, near, far, pad, mh = cfg
+        opacity_flat = opacity.reshape(-1)
+        records, zkey, visible, scan = ext.fused_preprocess_forward(
+            xyz, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, H, W, near, far, pad, mh)
+        total = int(scan[-1].item()) if xyz.shape[0] > 0 else 0  # the one host sync
+        M, P = total >> 32, total & 0xFFFFFFFF
+        ids_sorted, ranges, stream_rec, vis_idx, uv = ext.fused_bin(records, zkey, visible, scan, M, P, H, W, mh)
+        state.N, state.M, state.P, state.H, state.W = xyz.shape[0], M, P, H, W
+        state.visible, state.vis_idx = visible, vis_idx.long()  # int64: index_copy_ needs it
+        state.ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec
+        carrier = torch.empty(9 * xyz.shape[0], dtype=xyz.dtype, device=xyz.device)
+        ctx.state = state
+        ctx.has_sh = sh is not None
+        ctx.save_for_backward(xyz, quaternion, scale, opacity_flat, sh, camera_T_world, K)
+        return uv, carrier
+
+    @staticmethod
+    def backward(ctx, grad_uv, grad_carrier):
+        xyz, quaternion, scale, opacity_flat, sh, camera_T_world, K = ctx.saved_tensors
+        st = ctx.state
+        N = st.N
+        if grad_carrier is None:
+            grad_carrier = torch.zeros(9 * N, dtype=xyz.dtype, device=xyz.device)
+        slab = grad_carrier.contiguous()
+        if grad_uv is not None and st.M > 0:
+            # total gradient on the compact uv (render contribution + anything upstream) replaces the
+            # uv section of the slab
+            slab[4 * N:6 * N].view(N, 2).index_copy_(0, st.vis_idx, grad_uv.contiguous())
+        grads = native().fused_preprocess_backward(slab, xyz, quaternion, scale, opacity_flat, sh,
+                                                   camera_T_world, K, st.visible)
+        g_xyz, g_q, g_s, g_o, g_dc = grads[:5]
+        g_sh = grads[5] if ctx.has_sh else None
+        return g_xyz, g_q, g_s, g_o.view(-1, 1), g_dc, g_sh, None, None, None, None
+
+
+class _CompositeTiles(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, uv, carrier, background_rgb, state):
+        image, n_pp, w_pp = native().fused_render_forward(state.stream_rec, state.ranges, background_rgb,
+                                                          state.H, state.W)
+        state.n_per_pixel, state.w_per_pixel, state.background = n_pp, w_pp, background_rgb
+        ctx.state = state
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        st = ctx.state
+        slab = native().fused_render_backward(grad_image.contiguous(), st.N, st.stream_rec, st.ids_sorted,
+                                              st.ranges, st.background, st.n_per_pixel, st.w_per_pixel)
+        N = st.N
+        grad_uv = slab[4 * N:6 * N].view(N, 2).index_select(0, st.vis_idx)
+        return grad_uv, slab, None, None
+
+
+def rasterize(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist,
+              use_sh_precompute, background_rgb, return_state=False):
+    if gaussians.sh is not None and not use_sh_precompute:
+        return rasterize_unfused(gaussians, camera_T_world, camera, near_thresh, far_thresh,
+                                 cull_mask_padding, mh_dist, use_sh_precompute, background_rgb)
+    if gaussians.xyz.dtype != torch.float32:
+        raise TypeError("the fused rasterizer is fp32; use rasterize_unfused for float64 inputs")
+    state = _ViewState()
+    cfg = (int(camera.height), int(camera.width), float(near_thresh), float(far_thresh),
+           float(cull_mask_padding), float(mh_dist))
+    uv, carrier = _ProjectGaussians.apply(
+        gaussians.xyz.contiguous(), gaussians.quaternion.contiguous(), gaussians.scale.contiguous(),
+        gaussians.opacity.contiguous(), gaussians.rgb.contiguous(),
+        None if gaussians.sh is None else gaussians.sh.contiguous(),
+        camera_T_world.contiguous(), camera.K.contiguous(), state, cfg)
+    image = _CompositeTiles.apply(uv, carrier, background_rgb.contiguous(), state)
+    culling_mask = state.visible == 0
+    if return_state:
+        return image, culling_mask, uv, state
+    return image, culling_mask, uv
+
+
+def rasterize_unfused(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist,
+                      use_sh_precompute, background_rgb):
+    """Operator-by-operator evaluation, one native op per reference op (any dtype, any SH mode)."""
+    xyz_cam = transform_points_torch(gaussians.xyz, camera_T_world)
+    uv = CameraPointProjection.apply(xyz_cam, camera.K)
+    z = xyz_cam[:, 2]
+    culling_mask = (
+        (z < near_thresh) | (z > far_thresh)
+        | (uv[:, 0] < -1 * cull_mask_padding) | (uv[:, 0] > camera.width + cull_mask_padding)
+        | (uv[:, 1] < -1 * cull_mask_padding) | (uv[:, 1] > camera.height + cull_mask_padding)
+    )
+    keep = ~culling_mask
+    uv, xyz_cam = uv[keep, :], xyz_cam[keep, :]
+    xyz_w = gaussians.xyz[keep, :]
+    opacity = torch.sigmoid(gaussians.opacity[keep])
+    rgb = gaussians.rgb[keep, :]
+    sh = None if gaussians.sh is None else gaussians.sh[keep, :]
+
+    sigma_world = ComputeSigmaWorld.apply(gaussians.quaternion[keep, :], gaussians.scale[keep, :])
+    J = ComputeProjectionJacobian.apply(xyz_cam, camera.K)
+    conic = ComputeConic.apply(sigma_world, J, camera_T_world)
+
+    tiles = Tiles(camera.height, camera.width, uv.device)
+    sorted_idx, tile_ranges = get_splats(uv.detach(), tiles, conic.detach(), xyz_cam.detach(), mh_dist)
+
+    rays = torch.zeros(1, 1, 1, dtype=gaussians.xyz.dtype, device=gaussians.xyz.device)
+    if sh is not None:
+        coeffs = torch.cat((rgb.unsqueeze(dim=2), sh), dim=2)
+        if use_sh_precompute:
+            render_rgb = PrecomputeRGBFromSH.apply(coeffs, xyz_w, torch.inverse(camera_T_world).contiguous())
+        else:
+            render_rgb = coeffs
+            rays = compute_rays_in_world_frame(camera, camera_T_world)
+    else:
+        render_rgb = rgb
+    image = RenderImage.apply(render_rgb, opacity, uv, conic, rays, tile_ranges, sorted_idx,
+                              (camera.height, camera.width), background_rgb)
+    return image, culling_mask, uv

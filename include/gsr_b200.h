@@ -1,0 +1,226 @@
+/* gsr_b200.h — C ABI of the B200-native Gaussian-splat rasterizer hot path.
+ *
+ * This is the drop-in boundary: every entry point below is what the reference's
+ * pybind module `splat_cuda` (joeyan/gaussian_splatting, src/bindings.cpp:118-159)
+ * binds for the rasterization path, restated as plain C: device pointers, sizes,
+ * a stream handle, int status (0 = ok, otherwise a cudaError_t value, or
+ * GSR_ERR_* below for argument errors).  No torch types cross this line.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - tensors are dense row-major with the shapes the reference uses;
+ *   - `dtype` is GSR_F32 or GSR_F64 for the entry points the reference
+ *     instantiates for both (its gradcheck tests run in fp64);
+ *   - `stream` is a cudaStream_t passed as void*; nothing here synchronizes
+ *     (the reference calls cudaDeviceSynchronize() in most wrappers, e.g.
+ *     src/render.cu:421 — observationally equivalent for stream-ordered callers);
+ *   - outputs are caller-allocated; gradient outputs of the render backward are
+ *     ACCUMULATED into (caller zero-fills), exactly like the reference
+ *     (splat_py/cuda_autograd_functions.py:195-198).
+ */
+#ifndef GSR_B200_H
+#define GSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_F32 0
+#define GSR_F64 1
+
+#define GSR_OK 0
+#define GSR_ERR_BAD_ARG (-1)
+#define GSR_ERR_UNSUPPORTED (-2)
+
+/* floats per packed splat record consumed by the tile renderers (48 bytes) */
+#define GSR_REC_FLOATS 12
+
+/* library identification: returns e.g. "gsr_b200 0.1 sm_100a" */
+const char* gsr_version(void);
+
+/* ------------------------------------------------------------------------
+ * Per-Gaussian operators (one call == one reference binding)
+ * ---------------------------------------------------------------------- */
+
+/* camera_projection_cuda — src/bindings.cpp:35, src/projection.cu:21-54
+ * xyz [N,3], K [3,3] -> uv [N,2] */
+int gsr_camera_projection(int dtype, int N, const void* xyz, const void* K, void* uv, void* stream);
+
+/* camera_projection_backward_cuda — src/bindings.cpp:37-42, src/projection_backward.cu:38-90
+ * writes xyz_grad_in [N,3] (rows with z <= 0 are left untouched) */
+int gsr_camera_projection_backward(int dtype, int N, const void* xyz, const void* K,
+                                   const void* uv_grad_out, void* xyz_grad_in, void* stream);
+
+/* compute_sigma_world_cuda — src/bindings.cpp:44-48, src/projection.cu:111-152
+ * quaternion [N,4] wxyz, scale [N,3] log -> sigma_world [N,3,3] */
+int gsr_compute_sigma_world(int dtype, int N, const void* quaternion, const void* scale,
+                            void* sigma_world, void* stream);
+
+/* compute_sigma_world_backward_cuda — src/bindings.cpp:50-56, src/projection_backward.cu:317-382 */
+int gsr_compute_sigma_world_backward(int dtype, int N, const void* quaternion, const void* scale,
+                                     const void* sigma_world_grad_out, void* quaternion_grad_in,
+                                     void* scale_grad_in, void* stream);
+
+/* compute_projection_jacobian_cuda — src/bindings.cpp:58, src/projection.cu:177-211
+ * xyz [N,3] camera frame, K -> J [N,2,3] */
+int gsr_compute_projection_jacobian(int dtype, int N, const void* xyz, const void* K, void* J,
+                                    void* stream);
+
+/* compute_projection_jacobian_backward_cuda — src/bindings.cpp:60-65, src/projection_backward.cu:122-166 */
+int gsr_compute_projection_jacobian_backward(int dtype, int N, const void* xyz, const void* K,
+                                             const void* jac_grad_out, void* xyz_grad_in, void* stream);
+
+/* compute_conic_cuda — src/bindings.cpp:67-72, src/projection.cu:259-311
+ * sigma_world [N,3,3], J [N,2,3], camera_T_world [4,4] -> conic [N,3] = [S00, S01+S10, S11] */
+int gsr_compute_conic(int dtype, int N, const void* sigma_world, const void* J,
+                      const void* camera_T_world, void* conic, void* stream);
+
+/* compute_conic_backward_cuda — src/bindings.cpp:74-81, src/projection_backward.cu:473-550 */
+int gsr_compute_conic_backward(int dtype, int N, const void* sigma_world, const void* J,
+                               const void* camera_T_world, const void* conic_grad_out,
+                               void* sigma_world_grad_in, void* J_grad_in, void* stream);
+
+/* precompute_rgb_from_sh_cuda — src/bindings.cpp:93-98, src/precompute_sh.cu:113-250
+ * xyz [N,3] world, sh_coeff [N,3,n_sh] (n_sh in {1,4,9,16}; n_sh==1 may be [N,3]),
+ * camera_T_world [4,4] (only the translation column is read; the caller passes the
+ * INVERSE pose, splat_py/rasterize.py:91-93) -> rgb [N,3] */
+int gsr_precompute_rgb_from_sh(int dtype, int N, int n_sh, const void* xyz, const void* sh_coeff,
+                               const void* camera_T_world, void* rgb, void* stream);
+
+/* precompute_rgb_from_sh_backward_cuda — src/bindings.cpp:100-105, src/precompute_sh.cu:252-389
+ * grad_rgb [N,3] -> grad_sh [N,3,n_sh] (no gradient to xyz, as in the reference) */
+int gsr_precompute_rgb_from_sh_backward(int dtype, int N, int n_sh, const void* xyz,
+                                        const void* camera_T_world, const void* grad_rgb,
+                                        void* grad_sh, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Tile binning: get_sorted_gaussian_list — src/bindings.cpp:83-91,
+ * src/tile_culling.cu:244-340.  Split in two because the number of
+ * (gaussian, tile) pairs P sizes the outputs: phase 1 counts and scans,
+ * the host reads P = offsets[N], phase 2 emits, sorts and builds tile ranges.
+ * ---------------------------------------------------------------------- */
+size_t gsr_binning_count_temp_bytes(int N);
+/* offsets: int32 [N+1], exclusive scan of tiles-per-gaussian (offsets[N] == P) */
+int gsr_binning_count(int N, const float* uvs, const float* conic, int n_tiles_x, int n_tiles_y,
+                      float mh_dist, int32_t* offsets, void* temp, size_t temp_bytes, void* stream);
+
+size_t gsr_binning_sort_temp_bytes(int P);
+/* xyz_camera_frame [N,3] (depth = column 2).  Outputs: sorted_gaussian_idx int32 [P] ordered by
+ * (tile, depth, gaussian index); tile_ranges int32 [n_tiles+1] (reference: splat_start_end_idx_by_tile_idx) */
+int gsr_binning_emit_sort(int N, int P, const float* uvs, const float* xyz_camera_frame,
+                          const float* conic, int n_tiles_x, int n_tiles_y, float mh_dist,
+                          const int32_t* offsets, int32_t* sorted_gaussian_idx, int32_t* tile_ranges,
+                          void* temp, size_t temp_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Tile renderers, fp32 / precomputed-RGB fast path (N_SH == 1):
+ * render_tiles_cuda / render_tiles_backward_cuda — src/bindings.cpp:3-33,
+ * src/render.cu:191-422, src/render_backward.cu:287-595.
+ *
+ * The kernels consume a depth-sorted, tile-contiguous stream of 48-byte splat
+ * records (GSR_REC_FLOATS floats per pair) that is staged into shared memory
+ * by TMA bulk copies.  gsr_pack_records builds that stream from the
+ * reference's per-Gaussian arrays.
+ * ---------------------------------------------------------------------- */
+/* uvs [N,2], opacity [N] (post-sigmoid), rgb [N,3], conic [N,3], sorted idx [P] -> records [P,12] */
+int gsr_pack_records(int P, const int32_t* sorted_gaussian_idx, const float* uvs,
+                     const float* opacity, const float* rgb, const float* conic, float* records,
+                     void* stream);
+
+/* records [P,12], tile_ranges [n_tiles+1], background [3] ->
+ * image [H,W,3], num_splats_per_pixel int32 [H,W], final_weight_per_pixel [H,W] */
+int gsr_render_forward(const float* records, const int32_t* tile_ranges, const float* background_rgb,
+                       int H, int W, int32_t* num_splats_per_pixel, float* final_weight_per_pixel,
+                       float* image, void* stream);
+
+/* + grad_image [H,W,3]; accumulates into grad_rgb [N,3], grad_opacity [N], grad_uv [N,2],
+ * grad_conic [N,3] at row sorted_gaussian_idx[p] */
+int gsr_render_backward(const float* records, const int32_t* sorted_gaussian_idx,
+                        const int32_t* tile_ranges, const float* background_rgb, int H, int W,
+                        const int32_t* num_splats_per_pixel, const float* final_weight_per_pixel,
+                        const float* grad_image, float* grad_rgb, float* grad_opacity,
+                        float* grad_uv, float* grad_conic, void* stream);
+
+/* General renderers: any dtype, any n_sh in {1,4,9,16} (per-pixel SH via view_dir_by_pixel
+ * [H,W,3]); same semantics as the reference's template instantiations
+ * (fp64: no +0.25 dilation, exp(), no 1/255 skip — src/render.cu:117-148). */
+int gsr_render_forward_generic(int dtype, int N, int n_sh, const void* uvs, const void* opacity,
+                               const void* rgb, const void* conic, const void* view_dir_by_pixel,
+                               const int32_t* tile_ranges, const int32_t* sorted_gaussian_idx,
+                               const void* background_rgb, int H, int W,
+                               int32_t* num_splats_per_pixel, void* final_weight_per_pixel,
+                               void* image, void* stream);
+int gsr_render_backward_generic(int dtype, int N, int n_sh, const void* uvs, const void* opacity,
+                                const void* rgb, const void* conic, const void* view_dir_by_pixel,
+                                const int32_t* tile_ranges, const int32_t* sorted_gaussian_idx,
+                                const void* background_rgb, int H, int W,
+                                const int32_t* num_splats_per_pixel,
+                                const void* final_weight_per_pixel, const void* grad_image,
+                                void* grad_rgb, void* grad_opacity, void* grad_uv, void* grad_conic,
+                                void* stream);
+
+/* render_depth_cuda — src/bindings.cpp:107-116, src/depth.cu:117-177 (fp32 only) */
+int gsr_render_depth(int N, const float* xyz_camera_frame, const float* uvs, const float* opacity,
+                     const float* conic, const int32_t* tile_ranges,
+                     const int32_t* sorted_gaussian_idx, float alpha_threshold, int H, int W,
+                     float* depth_image, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused path behind splat_py.rasterize.rasterize (splat_py/rasterize.py:18-112):
+ * one kernel does world->camera transform, frustum cull, pinhole projection,
+ * Sigma_world, Jacobian, 2-D covariance, sigmoid(opacity), SH->RGB and the tile
+ * count for every Gaussian; results are bit-identical to running the
+ * reference's operator chain on the survivors.
+ * ---------------------------------------------------------------------- */
+size_t gsr_preprocess_temp_bytes(int N);
+/* inputs: xyz [N,3], quaternion [N,4], scale [N,3], opacity_logit [N], rgb_dc [N,3],
+ *         sh_rest [N,3,n_sh_rest] (n_sh_rest in {0,3,8,15}; may be NULL when 0),
+ *         camera_T_world [4,4] and K [3,3] ON DEVICE.
+ * outputs (all indexed by ORIGINAL gaussian index):
+ *   records  float [N,12]   packed splat record (undefined for culled rows)
+ *   depth_key uint32 [N]    order-preserving key of camera-frame z
+ *   visible  uint8 [N]      1 = survives the frustum cull (culling_mask = !visible)
+ *   scan     uint64 [N]     INCLUSIVE scan of (visible << 32 | tiles_touched);
+ *                           scan[N-1] >> 32 == M, scan[N-1] & 0xffffffff == P */
+int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
+                           const float* scale, const float* opacity_logit, const float* rgb_dc,
+                           const float* sh_rest, const float* camera_T_world, const float* K, int H,
+                           int W, float near_thresh, float far_thresh, float cull_mask_padding,
+                           float mh_dist, float* records, uint32_t* depth_key, uint8_t* visible,
+                           uint64_t* scan, void* temp, size_t temp_bytes, void* stream);
+
+/* emits the (tile, depth) keys and original-gaussian ids of all P pairs, the compact list of
+ * visible gaussian ids vis_idx int32 [M] and the compacted uv [M,2] the reference returns */
+int gsr_emit_pairs(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
+                   const uint64_t* scan, int n_tiles_x, int n_tiles_y, float mh_dist,
+                   uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, void* stream);
+
+size_t gsr_sort_pairs_temp_bytes(int P);
+int gsr_sort_pairs(int P, int n_tiles, const uint64_t* keys_in, const uint32_t* ids_in,
+                   uint64_t* keys_out, uint32_t* ids_out, void* temp, size_t temp_bytes, void* stream);
+
+/* tile_ranges int32 [n_tiles+1] from sorted keys */
+int gsr_tile_ranges(int P, int n_tiles, const uint64_t* keys_sorted, int32_t* tile_ranges, void* stream);
+
+/* records_sorted[p] = records[ids_sorted[p]] (48-byte rows) */
+int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, float* records_sorted,
+                       void* stream);
+
+/* backward of the fused per-Gaussian stage.  grad_rgb/grad_opacity/grad_uv/grad_conic are indexed by
+ * ORIGINAL gaussian index (as accumulated by gsr_render_backward; an upstream gradient on the
+ * returned compact uv is scattered into grad_uv by the caller through vis_idx).  Writes dense
+ * parameter gradients for all N gaussians (zeros for culled ones). */
+int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
+                            const float* scale, const float* opacity_logit, const float* camera_T_world,
+                            const float* K, const uint8_t* visible, const float* grad_rgb,
+                            const float* grad_opacity, const float* grad_uv, const float* grad_conic,
+                            float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
+                            float* g_rgb_dc, float* g_sh_rest, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H */
