@@ -81,6 +81,7 @@ def main():
     ap.add_argument("--sh", type=int, default=3)
     ap.add_argument("--out", default="gpurun_out/parity.json")
     ap.add_argument("--no-timing", action="store_true")
+    ap.add_argument("--pose", choices=["yaw", "general"], default="general")
     args = ap.parse_args()
     dev = torch.device("cuda")
     rep = dict(args=vars(args), gpu=torch.cuda.get_device_name(0))
@@ -101,7 +102,21 @@ def main():
 
     g = synth.make_gaussians(args.n, args.res, sh_degree=args.sh, seed=0, device=dev)
     cam = synth.make_camera(args.res, device=dev)
-    T = synth.make_pose(1, 3, device=dev)  # non-trivial rotation
+    if args.pose == "yaw":
+        T = synth.make_pose(0, 3, device=dev)  # -3 degree yaw about (0,0,6)
+    else:  # general rigid pose: every entry of the 3x4 block is non-trivial
+        gq = torch.Generator().manual_seed(7)
+        q = torch.randn(4, generator=gq, dtype=torch.float64) * 0.05 + torch.tensor([1.0, 0, 0, 0], dtype=torch.float64)
+        q = q / q.norm()
+        w_, x_, y_, z_ = q.tolist()
+        R = torch.tensor([[1 - 2 * (y_ * y_ + z_ * z_), 2 * (x_ * y_ - z_ * w_), 2 * (x_ * z_ + y_ * w_)],
+                          [2 * (x_ * y_ + z_ * w_), 1 - 2 * (x_ * x_ + z_ * z_), 2 * (y_ * z_ - x_ * w_)],
+                          [2 * (x_ * z_ - y_ * w_), 2 * (y_ * z_ + x_ * w_), 1 - 2 * (x_ * x_ + y_ * y_)]],
+                         dtype=torch.float64)
+        T = torch.eye(4, dtype=torch.float64)
+        T[:3, :3] = R
+        T[:3, 3] = torch.tensor([0.13, -0.21, 0.37], dtype=torch.float64)
+        T = T.float().to(dev)
     H, W = cam.height, cam.width
     cfg = synth.DEFAULTS
     bg = torch.full((3,), 0.5, device=dev)

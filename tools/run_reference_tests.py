@@ -1,0 +1,62 @@
+"""Run the reference's OWN unittest files (installed copy under oracle/_ref/test) with its python
+package bound to either CUDA implementation:
+
+    python tools/run_reference_tests.py --impl b200   # reference splat_py + tests on THIS library (drop-in proof)
+    python tools/run_reference_tests.py --impl ref    # same tests on the compiled reference (sanity / stale tests)
+
+test_dataloader.py is skipped (it needs a dataset on the reference author's disk).
+Writes a JSON summary to --out.  Needs a GPU.
+"""
+from __future__ import annotations
+
+import argparse
+import io
+import json
+import sys
+import unittest
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+REF_DIR = ROOT / "oracle" / "_ref"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--impl", choices=["b200", "ref"], required=True)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    import torch  # noqa: F401
+
+    if args.impl == "b200":
+        import gaussian_splatting_b200 as g
+
+        g.install_as_splat_cuda()
+    else:
+        from oracle import ref_loader
+
+        sys.modules["splat_cuda"] = ref_loader._load_ref_ext()
+    sys.path.insert(0, str(REF_DIR))          # reference `splat_py`
+    sys.path.insert(0, str(REF_DIR / "test"))  # its fixtures module
+    names = ["test_projection", "test_cuda_autograd_functions", "test_tile_culling", "test_rasterize",
+             "test_rasterize_autograd", "test_depth", "test_structs", "test_utils"]
+    suite = unittest.TestSuite()
+    loader = unittest.TestLoader()
+    for n in names:
+        suite.addTests(loader.loadTestsFromName(n))
+    buf = io.StringIO()
+    res = unittest.TextTestRunner(stream=buf, verbosity=2).run(suite)
+    text = buf.getvalue()
+    print(text[-6000:])
+    summary = dict(impl=args.impl, run=res.testsRun, failures=[str(t[0]) for t in res.failures],
+                   errors=[str(t[0]) for t in res.errors], ok=res.wasSuccessful(),
+                   details={str(t[0]): t[1][-800:] for t in res.failures + res.errors})
+    print(json.dumps({k: summary[k] for k in ("impl", "run", "failures", "errors", "ok")}))
+    if args.out:
+        Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+        Path(args.out).write_text(json.dumps(summary, indent=1))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
