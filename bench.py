@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd views/s of the rasterizer hot path on synthetic 1080p / 3M-Gaussian / SH-3 scenes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|reference-cpu]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one view: rasterize() forward + backward of the image
+against a fixed upstream gradient.  Views shard across ranks (rank r renders view step*N + r of a ring
+of poses; Gaussians are replicated; no collective on the raster path) -> weak scaling.  Rank 0 prints
+ONE JSON line (contract: see the round prompt / DESIGN.md "Measurement").
+
+  value     views/s, all inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       views/s through the public API with HOST buffers: per step the pose, intrinsics and the
+            upstream image gradient are copied from pinned host memory and the rendered image is read
+            back to pinned host memory inside the timed region
+  roofline  render-backward kernel: algorithmic bytes (76 B per consumed pair + 20 B per pixel,
+            SURVEY.md §8(d)) / CUDA-event duration, against the measured HBM peak
+  cpu_baseline  the CPU oracle (port of the reference's algorithm) on a bounded sample, rank 0, N=1
+
+--impl reference      the UNMODIFIED reference (its CUDA extension compiled into oracle/_ref, its own
+                      splat_py.rasterize) on the same scene/poses on this GPU — the number the ">= 2x the
+                      reference's own CUDA rasterizer" target is defined against.  The reference has no CPU
+                      implementation of this path; when oracle/_ref is absent this falls back to
+--impl reference-cpu  the CPU oracle port on the host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "fwd+bwd views/sec @1080p, 3M Gaussians, SH deg 3"
+N_GAUSS = 3_000_000
+RES = "1080p"
+SH_DEGREE = 3
+N_POSES = 8
+MY_KERNELS = ["k_preprocess_fwd", "k_emit_pairs_fused", "k_tile_ranges", "k_gather_records", "k_render_fwd",
+              "k_render_bwd", "k_preprocess_bwd"]
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (profiling recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = Path(f"/tmp/gsr_clocks_{os.getpid()}.csv")
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in self.path.read_text().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_scene(dev):
+    import torch
+
+    from gaussian_splatting_b200 import synth
+
+    g = synth.make_gaussians(N_GAUSS, RES, sh_degree=SH_DEGREE, seed=0, device=dev, requires_grad=True)
+    cam = synth.make_camera(RES, device=dev)
+    poses_host = [synth.make_pose(v, N_POSES).pin_memory() for v in range(N_POSES)]
+    poses = [p.to(dev) for p in poses_host]
+    G_host = synth.make_upstream_grad(RES).pin_memory()
+    G = G_host.to(dev)
+    bg = torch.full((3,), 0.5, device=dev)
+    return g, cam, poses, poses_host, G, G_host, bg
+
+
+def zero_grads(g):
+    for p in (g.xyz, g.rgb, g.opacity, g.scale, g.quaternion, g.sh):
+        if p is not None:
+            p.grad = None
+
+
+def timed_steps(step_fn, steps, warmup, world, dev):
+    """W warm-up steps, then K steps bracketed by barrier + synchronize; returns max-over-ranks ms."""
+    import torch
+    import torch.distributed as dist
+
+    for i in range(warmup):
+        step_fn(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step_fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def run_b200(args, rank, world, local):
+    import torch
+
+    from gaussian_splatting_b200 import synth
+    from gaussian_splatting_b200.rasterize import rasterize
+
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    g, cam, poses, poses_host, G, G_host, bg = build_scene(dev)
+    cfg = synth.DEFAULTS
+    K_host = cam.K.cpu().pin_memory()
+    image_host = torch.empty(cam.height, cam.width, 3).pin_memory()
+
+    def view_of(i):
+        return (i * world + rank) % N_POSES
+
+    def step_resident(i):
+        zero_grads(g)
+        image, _, _ = rasterize(g, poses[view_of(i)], cam, cfg["near_thresh"], cfg["far_thresh"],
+                                cfg["cull_mask_padding"], cfg["mh_dist"], True, bg)
+        image.backward(G)
+
+    h2d_bytes = poses_host[0].numel() * 4 + K_host.numel() * 4 + G_host.numel() * 4
+    d2h_bytes = image_host.numel() * 4
+
+    def step_e2e(i):
+        from gaussian_splatting_b200.structs import Camera
+
+        zero_grads(g)
+        T_dev = poses_host[view_of(i)].to(dev, non_blocking=True)
+        K_dev = K_host.to(dev, non_blocking=True)
+        G_dev = G_host.to(dev, non_blocking=True)
+        image, _, _ = rasterize(g, T_dev, Camera(cam.width, cam.height, K_dev), cfg["near_thresh"], cfg["far_thresh"],
+                                cfg["cull_mask_padding"], cfg["mh_dist"], True, bg)
+        image_host.copy_(image.detach(), non_blocking=True)
+        image.backward(G_dev)
+        torch.cuda.synchronize()  # the step's result is on the host before the next step starts
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res = timed_steps(step_resident, args.steps, args.warmup, world, dev)
+    ms_e2e = timed_steps(step_e2e, args.steps, args.warmup, world, dev)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- per-stage profile + scene statistics (rank 0; separate from the timed regions) ----
+    roofline, stages, stats = None, {}, {}
+    if rank == 0:
+        prof = []
+        n_prof = max(3, min(args.steps, 10))
+        last_state = None
+        for i in range(n_prof):
+            zero_grads(g)
+            image, _, _, st = rasterize(g, poses[view_of(i)], cam, cfg["near_thresh"], cfg["far_thresh"],
+                                        cfg["cull_mask_padding"], cfg["mh_dist"], True, bg, return_state=True,
+                                        profile=prof)
+            image.backward(G)
+            last_state = st
+        torch.cuda.synchronize()
+        acc = {}
+        for name, e0, e1 in prof:
+            acc.setdefault(name, []).append(e0.elapsed_time(e1))
+        stages = {k: statistics.mean(v) for k, v in acc.items()}
+        H, W = cam.height, cam.width
+        st = last_state
+        npp = st.n_per_pixel
+        Hp, Wp = (H + 15) // 16 * 16, (W + 15) // 16 * 16
+        pad = torch.zeros(Hp, Wp, dtype=npp.dtype, device=dev)
+        pad[:H, :W] = npp
+        tile_max = pad.view(Hp // 16, 16, Wp // 16, 16).amax(dim=(1, 3))
+        P_used = int(tile_max.sum().item())
+        stats = dict(N=st.N, M=st.M, P=st.P, P_consumed_by_render_bwd=P_used,
+                     splats_per_tile_mean=st.P / ((Hp // 16) * (Wp // 16)),
+                     mean_splats_walked_per_pixel=float(npp.float().mean().item()))
+        peaks = {}
+        pf = ROOT / "MEASURED_PEAKS.json"
+        if pf.exists():
+            peaks = json.loads(pf.read_text())
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = 76.0 * P_used + 20.0 * H * W
+        dur_ms = stages.get("render_bwd", float("nan"))
+        achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
+        roofline = dict(kernel="k_render_bwd", bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
+                        frac=achieved / peak, traffic=None,
+                        peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                        algorithmic_bytes=alg_bytes, duration_ms=dur_ms,
+                        note="76 B per (gaussian,tile) pair the kernel has to visit + 20 B per pixel")
+
+    cpu = cpu_baseline_leg(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+
+    if rank != 0:
+        return
+    views = args.steps * world
+    value = views / (ms_res * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic 3M Gaussians, 1080p, SH deg 3 (BASELINE.json configs[2]/[3]); one view "
+                               "per GPU per step, ring of 8 poses (3 deg yaw steps), fwd + bwd of image against a "
+                               "fixed upstream gradient",
+                   "gaussians": N_GAUSS, "image": "1920x1080", "sh_degree": SH_DEGREE, "views_per_step": world,
+                   "parallelism": f"views sharded 1 per GPU x{world}, gaussians replicated, no collective",
+                   "l2": "per-step inputs (708 MB of parameters) exceed the 126 MB L2; no flush needed",
+                   "scene": stats, "stage_ms": stages},
+        "clocks": clocks,
+        "e2e": {"value": views / (ms_e2e * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": len(MY_KERNELS) * args.steps, "kernels": MY_KERNELS,
+        "roofline": roofline, "cpu_baseline": cpu, "impl": "b200",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(args, rows=48):
+    """The CPU oracle (port of the reference's algorithm) on a bounded sample of the bench workload:
+    the whole per-gaussian stage and tile binning for all 3M gaussians, the tile renderer forward +
+    backward on a `rows`-pixel band, scaled to the full image height; per-gaussian backward in full."""
+    import numpy as np
+    import torch
+
+    from gaussian_splatting_b200 import synth
+    from oracle import cpu_oracle as orc
+
+    t_all = time.time()
+    g = synth.make_gaussians(N_GAUSS, RES, sh_degree=SH_DEGREE, seed=0)
+    cam = synth.make_camera(RES)
+    T = synth.make_pose(0, N_POSES)
+    a = lambda t: t.detach().numpy()  # noqa: E731
+    H, W = cam.height, cam.width
+    orc.lib()
+    t0 = time.time()
+    pg = orc.project(a(g.xyz), a(g.quaternion), a(g.scale), a(g.opacity), a(g.rgb), a(g.sh), a(T), a(cam.K), H, W,
+                     0.3, 500.0, 100.0)
+    t_proj = time.time() - t0
+    keep = pg.visible.astype(bool)
+    uv, conic, xyz_cam, opa, rgb = pg.uv[keep], pg.conic[keep], pg.xyz_cam[keep], pg.opacity[keep], pg.rgb[keep]
+    t0 = time.time()
+    sorted_idx, ranges = orc.tile_lists(uv, xyz_cam, conic, (W + 15) // 16, (H + 15) // 16, 3.0)
+    t_bin = time.time() - t0
+    band = (512, 512 + rows)
+    bgc = np.full(3, 0.5, np.float32)
+    t0 = time.time()
+    image, n, w = orc.render_forward(uv, opa, rgb, conic, None, ranges, sorted_idx, bgc, H, W, rows=band)
+    t_fwd = time.time() - t0
+    G = a(synth.make_upstream_grad(RES))
+    t0 = time.time()
+    gr = orc.render_backward(uv, opa, rgb, conic, None, ranges, sorted_idx, bgc, n, w, G, rows=band)
+    t_bwd = time.time() - t0
+    scale = H / rows
+    est = t_proj * 2.0 + t_bin + (t_fwd + t_bwd) * scale  # per-gaussian backward ~ per-gaussian forward
+    return {"value": 1.0 / est, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"CPU oracle (oracle/gsr_oracle.c, OpenMP x{os.cpu_count()}): per-gaussian stage + tile binning "
+                      f"for all {N_GAUSS} gaussians, tile renderer fwd+bwd on a {rows}-row band scaled x{scale:.1f}",
+            "seconds": {"project": t_proj, "binning": t_bin, "render_fwd_band": t_fwd, "render_bwd_band": t_bwd,
+                        "wall": time.time() - t_all}}
+
+
+def run_reference(args, rank, world, local):
+    """The unmodified reference on this GPU (oracle/_ref), rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        return run_reference_cpu(args, rank)
+    import torch
+
+    from gaussian_splatting_b200 import synth
+
+    ref_loader.load_reference()
+    ref_ras = sys.modules["splat_py_ref.rasterize"]
+    ref_structs = sys.modules["splat_py_ref.structs"]
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    g, cam, poses, poses_host, G, G_host, bg = build_scene(dev)
+    gaus = ref_structs.Gaussians(g.xyz, g.rgb, g.opacity, g.scale, g.quaternion, g.sh)
+    camr = ref_structs.Camera(cam.width, cam.height, cam.K)
+    cfg = synth.DEFAULTS
+
+    def step(i):
+        zero_grads(g)
+        image, _, _ = ref_ras.rasterize(gaus, poses[i % N_POSES], camr, cfg["near_thresh"], cfg["far_thresh"],
+                                        cfg["cull_mask_padding"], cfg["mh_dist"], True, bg)
+        image.backward(G)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed_steps(step, args.steps, args.warmup, 1, dev)
+    clocks = sampler.stop()
+    value = args.steps / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "synthetic 3M Gaussians, 1080p, SH deg 3; same scene/poses as the b200 arm",
+                   "how": "unmodified joeyan/gaussian_splatting: its CUDA extension compiled for sm_100 "
+                          "(oracle/_ref) driven by its own splat_py.rasterize.rasterize + backward, on GPU 0"},
+        "clocks": clocks,
+        "cpu_baseline": {"value": value, "unit": "views/s", "cores": 0, "kind": "reference",
+                         "sample": "full workload on the GPU: the reference implements this path only in CUDA "
+                                   "(no CPU implementation exists); see --impl reference-cpu for the CPU port"},
+        "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_cpu(args, rank):
+    if rank != 0:
+        return
+    cpu = cpu_baseline_leg(args)
+    line = {
+        "metric": METRIC, "value": cpu["value"], "unit": "views/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "synthetic 3M Gaussians, 1080p, SH deg 3 (bounded sample, see cpu_baseline.sample)"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cpu"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    rank, world, local = dist_env()
+    if args.impl == "reference-cpu":
+        return run_reference_cpu(args, rank)
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    if world > 1:
+        import torch.distributed as dist
+
+        if args.impl == "reference":
+            if rank == 0:
+                run_reference(args, rank, world, local)
+            return
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world, local)
+        else:
+            run_b200(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,7 +40,29 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
-                 "n_per_pixel", "w_per_pixel", "background", "stats")
+                 "n_per_pixel", "w_per_pixel", "background", "profile")
+
+    def __init__(self, profile=None):
+        self.profile = profile  # optional list: (stage name, start event, end event) per native call
+
+
+class _stage:
+    """CUDA-event bracket around one native stage (only when the caller asked for a profile)."""
+
+    def __init__(self, state, name):
+        self.rec = state.profile
+        self.name = name
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            self.e1.record()
+            self.rec.append((self.name, self.e0, self.e1))
 
 
 class _ProjectGaussians(torch.autograd.Function):
@@ -49,11 +71,13 @@ class _ProjectGaussians(torch.autograd.Function):
         ext = native()
         H, W, near, far, pad, mh = cfg
         opacity_flat = opacity.reshape(-1)
-        records, zkey, visible, scan = ext.fused_preprocess_forward(
-            xyz, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, H, W, near, far, pad, mh)
+        with _stage(state, "preprocess_fwd"):
+            records, zkey, visible, scan = ext.fused_preprocess_forward(
+                xyz, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, H, W, near, far, pad, mh)
         total = int(scan[-1].item()) if xyz.shape[0] > 0 else 0  # the one host sync
         M, P = total >> 32, total & 0xFFFFFFFF
-        ids_sorted, ranges, stream_rec, vis_idx, uv = ext.fused_bin(records, zkey, visible, scan, M, P, H, W, mh)
+        with _stage(state, "bin_sort_gather"):
+            ids_sorted, ranges, stream_rec, vis_idx, uv = ext.fused_bin(records, zkey, visible, scan, M, P, H, W, mh)
         state.N, state.M, state.P, state.H, state.W = xyz.shape[0], M, P, H, W
         state.visible, state.vis_idx = visible, vis_idx.long()  # int64: index_copy_ needs it
         state.ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec
@@ -75,8 +99,9 @@ class _ProjectGaussians(torch.autograd.Function):
             # total gradient on the compact uv (render contribution + anything upstream) replaces the
             # uv section of the slab
             slab[4 * N:6 * N].view(N, 2).index_copy_(0, st.vis_idx, grad_uv.contiguous())
-        grads = native().fused_preprocess_backward(slab, xyz, quaternion, scale, opacity_flat, sh,
-                                                   camera_T_world, K, st.visible)
+        with _stage(st, "preprocess_bwd"):
+            grads = native().fused_preprocess_backward(slab, xyz, quaternion, scale, opacity_flat, sh,
+                                                       camera_T_world, K, st.visible)
         g_xyz, g_q, g_s, g_o, g_dc = grads[:5]
         g_sh = grads[5] if ctx.has_sh else None
         return g_xyz, g_q, g_s, g_o.view(-1, 1), g_dc, g_sh, None, None, None, None
@@ -85,8 +110,9 @@ class _ProjectGaussians(torch.autograd.Function):
 class _CompositeTiles(torch.autograd.Function):
     @staticmethod
     def forward(ctx, uv, carrier, background_rgb, state):
-        image, n_pp, w_pp = native().fused_render_forward(state.stream_rec, state.ranges, background_rgb,
-                                                          state.H, state.W)
+        with _stage(state, "render_fwd"):
+            image, n_pp, w_pp = native().fused_render_forward(state.stream_rec, state.ranges, background_rgb,
+                                                              state.H, state.W)
         state.n_per_pixel, state.w_per_pixel, state.background = n_pp, w_pp, background_rgb
         ctx.state = state
         return image
@@ -94,21 +120,22 @@ class _CompositeTiles(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_image):
         st = ctx.state
-        slab = native().fused_render_backward(grad_image.contiguous(), st.N, st.stream_rec, st.ids_sorted,
-                                              st.ranges, st.background, st.n_per_pixel, st.w_per_pixel)
+        with _stage(st, "render_bwd"):
+            slab = native().fused_render_backward(grad_image.contiguous(), st.N, st.stream_rec, st.ids_sorted,
+                                                  st.ranges, st.background, st.n_per_pixel, st.w_per_pixel)
         N = st.N
         grad_uv = slab[4 * N:6 * N].view(N, 2).index_select(0, st.vis_idx)
         return grad_uv, slab, None, None
 
 
 def rasterize(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist,
-              use_sh_precompute, background_rgb, return_state=False):
+              use_sh_precompute, background_rgb, return_state=False, profile=None):
     if gaussians.sh is not None and not use_sh_precompute:
         return rasterize_unfused(gaussians, camera_T_world, camera, near_thresh, far_thresh,
                                  cull_mask_padding, mh_dist, use_sh_precompute, background_rgb)
     if gaussians.xyz.dtype != torch.float32:
         raise TypeError("the fused rasterizer is fp32; use rasterize_unfused for float64 inputs")
-    state = _ViewState()
+    state = _ViewState(profile)
     cfg = (int(camera.height), int(camera.width), float(near_thresh), float(far_thresh),
            float(cull_mask_padding), float(mh_dist))
     uv, carrier = _ProjectGaussians.apply(

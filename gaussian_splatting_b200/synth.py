@@ -16,6 +16,7 @@ SH0 = 0.28209479177387814
 RESOLUTIONS = {
     "1080p": (1080, 1920, 1200.0),
     "720p": (720, 1280, 800.0),
+    "small": (192, 320, 200.0),
     "tiny": (64, 64, 60.0),
 }
 

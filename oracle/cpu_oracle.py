@@ -103,7 +103,7 @@ def tile_lists(uvs, xyz_cam, conic, n_tiles_x, n_tiles_y, mh_dist):
     return sorted_idx[:P], ranges
 
 
-def render_forward(uvs, opacity, rgb, conic, view_dirs, ranges, sorted_idx, background, H, W):
+def render_forward(uvs, opacity, rgb, conic, view_dirs, ranges, sorted_idx, background, H, W, rows=None):
     """render_tiles_cuda (src/render.cu:191-422): -> (image [H,W,3], n [H,W] int32, wlast [H,W])."""
     dt = uvs.dtype
     c = lambda a: np.ascontiguousarray(a, dtype=dt)  # noqa: E731
@@ -112,14 +112,15 @@ def render_forward(uvs, opacity, rgb, conic, view_dirs, ranges, sorted_idx, back
     n = np.zeros((H, W), np.int32)
     w = np.zeros((H, W), dt)
     vd = c(view_dirs) if n_sh > 1 else None
+    r0, r1 = (0, H) if rows is None else rows
     fn = getattr(lib(), "orc_render_forward" + _suffix(dt))
     fn(C.c_int(H), C.c_int(W), C.c_int(n_sh), _p(c(uvs)), _p(c(opacity).reshape(-1)), _p(c(rgb)), _p(c(conic)), _p(vd),
        _p(np.ascontiguousarray(ranges, np.int32)), _p(np.ascontiguousarray(sorted_idx, np.int32)), _p(c(background)),
-       _p(n), _p(w), _p(image))
+       C.c_int(r0), C.c_int(r1), _p(n), _p(w), _p(image))
     return image, n, w
 
 
-def render_backward(uvs, opacity, rgb, conic, view_dirs, ranges, sorted_idx, background, n, w, grad_image):
+def render_backward(uvs, opacity, rgb, conic, view_dirs, ranges, sorted_idx, background, n, w, grad_image, rows=None):
     """render_tiles_backward_cuda (src/render_backward.cu:287-595): float64 sums
     -> (g_rgb [G,3(,K)], g_opacity [G,1], g_uv [G,2], g_conic [G,3])."""
     dt = uvs.dtype
@@ -133,11 +134,12 @@ def render_backward(uvs, opacity, rgb, conic, view_dirs, ranges, sorted_idx, bac
     g_conic = np.zeros((G, 3), np.float64)
     vd = c(view_dirs) if n_sh > 1 else None
     chunk = REF_CHUNK[(np.dtype(dt).type, n_sh)]
+    r0, r1 = (0, H) if rows is None else rows
     fn = getattr(lib(), "orc_render_backward" + _suffix(dt))
     fn(C.c_int(H), C.c_int(W), C.c_int(n_sh), C.c_int(chunk), _p(c(uvs)), _p(c(opacity).reshape(-1)), _p(c(rgb)),
        _p(c(conic)), _p(vd), _p(np.ascontiguousarray(ranges, np.int32)), _p(np.ascontiguousarray(sorted_idx, np.int32)),
-       _p(c(background)), _p(np.ascontiguousarray(n, np.int32)), _p(c(w)), _p(c(grad_image)), _p(g_rgb), _p(g_opa),
-       _p(g_uv), _p(g_conic))
+       _p(c(background)), C.c_int(r0), C.c_int(r1), _p(np.ascontiguousarray(n, np.int32)), _p(c(w)), _p(c(grad_image)),
+       _p(g_rgb), _p(g_opa), _p(g_uv), _p(g_conic))
     return g_rgb, g_opa, g_uv, g_conic
 
 

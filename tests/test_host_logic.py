@@ -1,0 +1,79 @@
+"""Host-side mirror of the reference's python modules (no GPU)."""
+import math
+
+import numpy as np
+import torch
+
+from gaussian_splatting_b200 import synth
+from gaussian_splatting_b200.structs import Camera, Gaussians, Tiles
+from gaussian_splatting_b200.utils import (compute_rays, compute_rays_in_world_frame, inverse_sigmoid_torch,
+                                           quaternion_to_rotation_torch, transform_points_torch)
+
+
+def test_tiles_1080p():
+    """test/test_structs.py:21-26"""
+    t = Tiles(1080, 1920, "cpu")
+    assert (t.image_height_padded, t.image_width_padded) == (1088, 1920)
+    assert (t.y_tiles_count, t.x_tiles_count, t.tile_count) == (68, 120, 8160)
+    t = Tiles(480, 640, "cpu")
+    assert (t.y_tiles_count, t.x_tiles_count) == (30, 40)
+
+
+def test_gaussians_container():
+    g = synth.make_gaussians(10, "tiny", sh_degree=3)
+    assert len(g) == 10 and g.sh.shape == (10, 3, 15)
+    g.filter_in_place(torch.arange(10) % 2 == 0)
+    assert len(g) == 5 and isinstance(g.xyz, torch.nn.Parameter)
+    extra = synth.make_gaussians(3, "tiny", sh_degree=3, seed=5)
+    g.append(extra.xyz, extra.rgb, extra.opacity, extra.scale, extra.quaternion, extra.sh)
+    assert len(g) == 8 and g.sh.shape == (8, 3, 15)
+
+
+def test_quaternion_to_rotation_is_orthonormal():
+    """test/test_utils.py (orthogonality check)"""
+    q = torch.randn(32, 4, dtype=torch.float64)
+    q = q / q.norm(dim=1, keepdim=True)
+    R = quaternion_to_rotation_torch(q)
+    eye = torch.eye(3, dtype=torch.float64).expand(32, 3, 3)
+    assert torch.allclose(R @ R.transpose(1, 2), eye, atol=1e-12)
+    assert torch.allclose(torch.linalg.det(R), torch.ones(32, dtype=torch.float64), atol=1e-12)
+
+
+def test_transform_round_trip():
+    T = synth.make_pose(0, 3, dtype=torch.float64)
+    pts = torch.randn(100, 3, dtype=torch.float64)
+    back = transform_points_torch(transform_points_torch(pts, T), torch.inverse(T))
+    assert torch.allclose(back, pts, atol=1e-12)
+    assert transform_points_torch(pts, T).is_contiguous()
+
+
+def test_rays():
+    cam = synth.make_camera("tiny", dtype=torch.float64)
+    r = compute_rays(cam)
+    assert r.shape == (64 * 64, 3) and torch.allclose(r.norm(dim=1), torch.ones(64 * 64, dtype=torch.float64))
+    # principal ray at (cx, cy) = (32, 32) is +z
+    assert torch.allclose(r[32 * 64 + 32], torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64))
+    rw = compute_rays_in_world_frame(cam, torch.eye(4, dtype=torch.float64))
+    assert rw.shape == (64, 64, 3) and torch.allclose(rw.reshape(-1, 3), r)
+
+
+def test_inverse_sigmoid_clip():
+    x = torch.tensor([0.0, 0.5, 1.0])
+    y = inverse_sigmoid_torch(x)
+    assert math.isclose(y[0].item(), math.log(1e-4 / (1 - 1e-4)), rel_tol=1e-5)
+    assert y[1].item() == 0.0
+    assert math.isclose(y[2].item(), -y[0].item(), rel_tol=1e-3)
+
+
+def test_synth_is_deterministic_and_shaped():
+    a = synth.make_gaussians(1000, "720p", seed=0)
+    b = synth.make_gaussians(1000, "720p", seed=0)
+    for name in ("xyz", "quaternion", "scale", "opacity", "rgb", "sh"):
+        assert torch.equal(getattr(a, name), getattr(b, name))
+    assert a.xyz[:, 2].min() >= 1 and a.xyz[:, 2].max() <= 11
+    T = synth.make_pose(0, 1)
+    assert torch.equal(T, torch.eye(4))
+    T0, T2 = synth.make_pose(0, 3), synth.make_pose(2, 3)
+    assert torch.allclose(T0[:3, :3], T2[:3, :3].T, atol=1e-6)  # +-3 degree yaw
+    G = synth.make_upstream_grad("tiny")
+    assert G.shape == (64, 64, 3) and abs(G.std().item() * 3 * 64 * 64 - 1) < 0.05
