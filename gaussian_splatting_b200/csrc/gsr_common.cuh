@@ -11,11 +11,15 @@ constexpr int TILE = 16;            // tile edge in pixels (splat_py/structs.py:
 constexpr int TILE_PIXELS = 256;
 constexpr int REC = GSR_REC_FLOATS; // floats per splat record
 
-// record slots
+// record slots: three 16-byte lanes
+//   q0 = (u, v, r2skip, opacity)   everything the per-warp footprint test needs
+//   q1 = (a, 2b, c, det)           a = conic0 + 0.25, 2b = conic1, c = conic2 + 0.25, det = a*c - b*b
+//   q2 = (rcp, colR, colG, colB)   rcp = Newton-refined 1/det (0 when det is outside the safe range),
+//                                  col = SH_0 * rgb
 enum RecSlot {
-    R_U = 0, R_V = 1, R_A = 2, R_B2 = 3,     // mean, a = conic0 + 0.25, b2 = 2*b = conic1
-    R_C = 4, R_DET = 5, R_RCP = 6, R_RDET = 7, // c = conic2 + 0.25, det, refined 1/det, fl32(1.0/det)
-    R_OPA = 8, R_CR = 9, R_CG = 10, R_CB = 11  // opacity (post-sigmoid), SH_0 * rgb
+    R_U = 0, R_V = 1, R_R2 = 2, R_OPA = 3,
+    R_A = 4, R_B2 = 5, R_C = 6, R_DET = 7,
+    R_RCP = 8, R_CR = 9, R_CG = 10, R_CB = 11
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

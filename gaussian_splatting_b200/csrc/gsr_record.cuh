@@ -5,28 +5,51 @@
 
 namespace gsr {
 
+// Squared pixel distance beyond which this splat provably contributes nothing to a pixel, i.e.
+// alpha = opacity * exp(-mh/2) stays below the reference's 1/255 skip threshold:
+//   mh = d^T Sigma^-1 d >= |d|^2 / lambda_max   and   alpha < t  <=  mh > 2 ln(opacity / t).
+// The bound is inflated (6% + a condition-number term + 1 px^2) so that neither the fp32 rounding of
+// mh in the kernels nor the few-ulp error of ex2.approx can make a culled pixel pass the reference's
+// test; culling is therefore invisible in the results (checked bitwise against the reference).
+// Returns -1 when the splat can never reach the threshold, +inf when nothing can be proven.
+__device__ __forceinline__ float cull_radius_sq(float a, float bh, float c, float det, float opa) {
+    if (!(opa > 0.0039137f)) return -1.0f;  // 0.998 / 255: opacity * g <= opacity can never reach 1/255
+    if (!(det > 0.0f) || !(a > 0.0f) || !(c > 0.0f)) return __int_as_float(0x7f800000);
+    const float hd = 0.5f * (a - c);
+    const float lam = 0.5f * (a + c) + sqrtf(hd * hd + bh * bh);  // lambda_max of [[a,b],[b,c]]
+    const float tau = fmaxf(2.0f * logf(opa * 255.6f), 0.0f);
+    const float r2 = (1.06f + 4e-6f * (lam * lam / det)) * tau * lam + 1.0f;
+    return (r2 == r2) ? r2 : __int_as_float(0x7f800000);
+}
+
 __device__ __forceinline__ void make_record(float u, float v, float c0, float c1, float c2, float opa,
                                             float r, float g, float b, float* __restrict__ rec) {
-    // a, b, c, det: src/render.cu:117-127 (fp32 branch: +0.25 dilation)
+    // a, b, c, det: src/render.cu:117-127 (fp32 branch: +0.25 dilation), rounding order of the reference build
     const float a = __fadd_rn(c0, 0.25f);
     const float c = __fadd_rn(c2, 0.25f);
     const float bh = __fmul_rn(c1, 0.5f);
     const float det = __fmaf_rn(a, c, -__fmul_rn(bh, bh));
-    // refined reciprocal used by the 3-FMA exact division in the forward kernel
-    float r0;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(det));
-    const float e = __fmaf_rn(-det, r0, 1.0f);
-    const float r1 = __fmaf_rn(r0, e, r0);
+    // 1/det refined by one Newton step: with it, q = num*rcp; q += rcp*fma(-det,q,num) is the correctly
+    // rounded IEEE quotient num/det (the fast path of the compiler's own division), valid while det and
+    // num stay far from the denormal/overflow range; rcp = 0 tells the kernel to use __fdiv_rn instead.
+    float rcp = 0.0f;
+    const float adet = fabsf(det);
+    if (adet > 1e-18f && adet < 1e18f) {
+        float r0;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(det));
+        const float e = __fmaf_rn(-det, r0, 1.0f);
+        rcp = __fmaf_rn(r0, e, r0);
+    }
     rec[R_U] = u;
     rec[R_V] = v;
+    rec[R_R2] = cull_radius_sq(a, bh, c, det, opa);
+    rec[R_OPA] = opa;
     rec[R_A] = a;
     rec[R_B2] = __fadd_rn(bh, bh);
     rec[R_C] = c;
     rec[R_DET] = det;
-    rec[R_RCP] = r1;
-    rec[R_RDET] = (float)(1.0 / (double)det);  // src/render_backward.cu:153
-    rec[R_OPA] = opa;
-    rec[R_CR] = __fmul_rn(r, GSR_SH0);  // sh_to_rgb with N_SH == 1: Y0 * rgb
+    rec[R_RCP] = rcp;
+    rec[R_CR] = __fmul_rn(r, GSR_SH0);  // sh_to_rgb with N_SH == 1: Y0 * rgb (src/spherical_harmonics.cuh:83)
     rec[R_CG] = __fmul_rn(g, GSR_SH0);
     rec[R_CB] = __fmul_rn(b, GSR_SH0);
 }

@@ -197,10 +197,10 @@ def main():
         out["uv_visible"] = bits_equal(rec[keep][:, 0:2], uv[keep])
         out["z_visible"] = bits_equal(zkey[keep], (xyz_cam[keep][:, 2].contiguous().view(torch.int32) | -2**31))
         conic = state["conic"][keep]
-        out["a"] = bits_equal(rec[keep][:, 2], conic[:, 0] + 0.25)
-        out["b2"] = bits_equal(rec[keep][:, 3], (conic[:, 1] * 0.5) * 2)
-        out["c"] = bits_equal(rec[keep][:, 4], conic[:, 2] + 0.25)
-        out["opacity"] = bits_equal(rec[keep][:, 8], torch.sigmoid(g.opacity[keep]).reshape(-1))
+        out["a"] = bits_equal(rec[keep][:, 4], conic[:, 0] + 0.25)
+        out["b2"] = bits_equal(rec[keep][:, 5], (conic[:, 1] * 0.5) * 2)
+        out["c"] = bits_equal(rec[keep][:, 6], conic[:, 2] + 0.25)
+        out["opacity"] = bits_equal(rec[keep][:, 3], torch.sigmoid(g.opacity[keep]).reshape(-1))
         total = int(scan[-1].item())
         out["M_scan"], out["P_scan"] = total >> 32, total & 0xFFFFFFFF
         return out

@@ -25,7 +25,38 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", choices=["b200", "ref"], required=True)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--module", default=None, help="run one test module in-process (used by the driver mode)")
+    ap.add_argument("--per-module-timeout", type=int, default=120)
     args = ap.parse_args()
+    names = ["test_projection", "test_tile_culling", "test_rasterize", "test_depth", "test_structs", "test_utils",
+             "test_cuda_autograd_functions", "test_rasterize_autograd"]
+    if args.module is None:
+        # driver mode: one subprocess per module, each with its own timeout, so a hang is isolated and named
+        import subprocess
+        import time
+
+        summary = dict(impl=args.impl, modules={})
+        for n in names:
+            t0 = time.time()
+            try:
+                pr = subprocess.run([sys.executable, __file__, "--impl", args.impl, "--module", n], capture_output=True,
+                                    text=True, timeout=args.per_module_timeout)
+                tail = (pr.stdout + pr.stderr)[-1500:]
+                status = "ok" if pr.returncode == 0 else f"rc={pr.returncode}"
+            except subprocess.TimeoutExpired as e:
+                tail = ((e.stdout or b"").decode(errors="ignore") + (e.stderr or b"").decode(errors="ignore"))[-1500:]
+                status = f"TIMEOUT after {args.per_module_timeout}s"
+            summary["modules"][n] = dict(status=status, seconds=round(time.time() - t0, 1), tail=tail)
+            print(n, status, f"{time.time() - t0:.1f}s", flush=True)
+            if args.out:
+                Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+                Path(args.out).write_text(json.dumps(summary, indent=1))
+        summary["ok"] = all(m["status"] == "ok" for m in summary["modules"].values())
+        print(json.dumps({k: v["status"] for k, v in summary["modules"].items()}))
+        if args.out:
+            Path(args.out).write_text(json.dumps(summary, indent=1))
+        return 0
+    names = [args.module]
     import torch  # noqa: F401
 
     if args.impl == "b200":
@@ -38,8 +69,6 @@ def main():
         sys.modules["splat_cuda"] = ref_loader._load_ref_ext()
     sys.path.insert(0, str(REF_DIR))          # reference `splat_py`
     sys.path.insert(0, str(REF_DIR / "test"))  # its fixtures module
-    names = ["test_projection", "test_cuda_autograd_functions", "test_tile_culling", "test_rasterize",
-             "test_rasterize_autograd", "test_depth", "test_structs", "test_utils"]
     suite = unittest.TestSuite()
     loader = unittest.TestLoader()
     for n in names:
@@ -52,10 +81,7 @@ def main():
                    errors=[str(t[0]) for t in res.errors], ok=res.wasSuccessful(),
                    details={str(t[0]): t[1][-800:] for t in res.failures + res.errors})
     print(json.dumps({k: summary[k] for k in ("impl", "run", "failures", "errors", "ok")}))
-    if args.out:
-        Path(args.out).parent.mkdir(parents=True, exist_ok=True)
-        Path(args.out).write_text(json.dumps(summary, indent=1))
-    return 0
+    return 0 if res.wasSuccessful() else 1
 
 
 if __name__ == "__main__":
