@@ -90,7 +90,8 @@ __device__ __forceinline__ void sh_rgb_fused(const float* __restrict__ dc, const
 
 template <int N_SH, bool HAS_SH>
 __global__ void __launch_bounds__(PRE_THREADS)
-    k_preprocess_fwd(int N, const float* __restrict__ xyz, const float* __restrict__ quat,
+    k_preprocess_fwd(int N, const float* __restrict__ xyz, const float* __restrict__ xyz_cam,
+                     const float* __restrict__ quat,
                      const float* __restrict__ scale, const float* __restrict__ opa_logit,
                      const float* __restrict__ rgb_dc, const float* __restrict__ sh_rest,
                      const float* __restrict__ Tdev, const float* __restrict__ Kdev, float width,
@@ -105,7 +106,11 @@ __global__ void __launch_bounds__(PRE_THREADS)
 
     const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
     float px, py, pz, u, v;
-    transform_point<float>(vc.T, x, y, z, px, py, pz);
+    if (xyz_cam != nullptr) {
+        px = xyz_cam[i * 3 + 0]; py = xyz_cam[i * 3 + 1]; pz = xyz_cam[i * 3 + 2];
+    } else {
+        transform_point<float>(vc.T, x, y, z, px, py, pz);
+    }
     project_uv<float>(px, py, pz, vc.K[0], vc.K[2], vc.K[4], vc.K[5], u, v);
     // splat_py/rasterize.py:38-49 (strict compares, fp32)
     const bool culled = (pz < near_t) | (pz > far_t) | (u < -pad) | (u > width + pad) | (v < -pad) |
@@ -262,7 +267,8 @@ size_t gsr_preprocess_temp_bytes(int N) {
     return align256(b) + align256(sizeof(uint64_t) * (size_t)(N > 0 ? N : 1));
 }
 
-int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
+int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* xyz_camera_frame,
+                           const float* quaternion,
                            const float* scale, const float* opacity_logit, const float* rgb_dc,
                            const float* sh_rest, const float* camera_T_world, const float* K, int H,
                            int W, float near_thresh, float far_thresh, float cull_mask_padding,
@@ -277,7 +283,8 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
     const int ntx = (W + TILE - 1) / TILE, nty = (H + TILE - 1) / TILE;
     const dim3 grid((N + PRE_THREADS - 1) / PRE_THREADS), block(PRE_THREADS);
 #define GSR_PRE_ARGS                                                                              \
-    N, xyz, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K, (float)W, (float)H, \
+    N, xyz, xyz_camera_frame, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K, (float)W, \
+        (float)H,                                                                                          \
         near_thresh, far_thresh, cull_mask_padding, mh_dist, ntx, nty, records, depth_key, visible, packed
     switch (n_sh_rest) {
         case 0: k_preprocess_fwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;

@@ -409,9 +409,10 @@ void render_depth_cuda(torch::Tensor xyz_camera_frame, torch::Tensor uvs, torch:
 
 // returns (records[N,12], depth_key[N] i32-viewed u32, visible[N] u8, scan[N] i64-viewed u64)
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_preprocess_forward(
-    torch::Tensor xyz, torch::Tensor quaternion, torch::Tensor scale, torch::Tensor opacity_logit,
-    torch::Tensor rgb_dc, c10::optional<torch::Tensor> sh_rest, torch::Tensor camera_T_world, torch::Tensor K,
-    int64_t H, int64_t W, double near_thresh, double far_thresh, double cull_mask_padding, double mh_dist) {
+    torch::Tensor xyz, c10::optional<torch::Tensor> xyz_camera_frame, torch::Tensor quaternion, torch::Tensor scale,
+    torch::Tensor opacity_logit, torch::Tensor rgb_dc, c10::optional<torch::Tensor> sh_rest,
+    torch::Tensor camera_T_world, torch::Tensor K, int64_t H, int64_t W, double near_thresh, double far_thresh,
+    double cull_mask_padding, double mh_dist) {
     CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(quaternion); CHECK_VALID_INPUT(scale); CHECK_VALID_INPUT(opacity_logit);
     CHECK_VALID_INPUT(rgb_dc); CHECK_VALID_INPUT(camera_T_world); CHECK_VALID_INPUT(K);
     CHECK_FLOAT_TENSOR(xyz); CHECK_FLOAT_TENSOR(quaternion); CHECK_FLOAT_TENSOR(scale);
@@ -424,6 +425,13 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
     TORCH_CHECK(opacity_logit.numel() == N, "opacity must have shape Nx1");
     TORCH_CHECK(rgb_dc.size(0) == N && rgb_dc.size(1) == 3, "rgb must have shape Nx3");
     TORCH_CHECK(camera_T_world.numel() == 16 && K.numel() == 9, "camera_T_world must be 4x4 and K 3x3");
+    const float* cam_ptr = nullptr;
+    if (xyz_camera_frame.has_value()) {
+        const torch::Tensor& pc = *xyz_camera_frame;
+        CHECK_VALID_INPUT(pc); CHECK_FLOAT_TENSOR(pc);
+        TORCH_CHECK(pc.dim() == 2 && pc.size(0) == N && pc.size(1) == 3, "xyz_camera_frame must have shape Nx3");
+        cam_ptr = pc.data_ptr<float>();
+    }
     int n_rest = 0;
     const float* sh_ptr = nullptr;
     if (sh_rest.has_value()) {
@@ -442,7 +450,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
     torch::Tensor scan = torch::empty({N}, opt.dtype(torch::kInt64));
     const size_t tb = gsr_preprocess_temp_bytes(N);
     torch::Tensor temp = torch::empty({(int64_t)tb}, opt.dtype(torch::kUInt8));
-    check_rc(gsr_preprocess_forward(N, n_rest, F32PTR(xyz), F32PTR(quaternion), F32PTR(scale),
+    check_rc(gsr_preprocess_forward(N, n_rest, F32PTR(xyz), cam_ptr, F32PTR(quaternion), F32PTR(scale),
                                     F32PTR(opacity_logit), F32PTR(rgb_dc), sh_ptr, F32PTR(camera_T_world),
                                     F32PTR(K), (int)H, (int)W, (float)near_thresh, (float)far_thresh,
                                     (float)cull_mask_padding, (float)mh_dist, F32PTR(records),

@@ -36,6 +36,9 @@ from .tile_culling import get_splats
 from .utils import compute_rays_in_world_frame, transform_points_torch
 
 
+IN_KERNEL_TRANSFORM = False
+
+
 class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
@@ -71,9 +74,13 @@ class _ProjectGaussians(torch.autograd.Function):
         ext = native()
         H, W, near, far, pad, mh = cfg
         opacity_flat = opacity.reshape(-1)
+        # camera-frame positions: by default formed exactly like the reference does (torch.matmul,
+        # splat_py/utils.py:60-72), because their bits decide tile membership and the 1/255 skip and the
+        # rounding order inside cuBLAS is not ours to pin; IN_KERNEL_TRANSFORM folds it into the kernel.
+        xyz_cam = None if IN_KERNEL_TRANSFORM else transform_points_torch(xyz, camera_T_world)
         with _stage(state, "preprocess_fwd"):
             records, zkey, visible, scan = ext.fused_preprocess_forward(
-                xyz, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, H, W, near, far, pad, mh)
+                xyz, xyz_cam, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, H, W, near, far, pad, mh)
         total = int(scan[-1].item()) if xyz.shape[0] > 0 else 0  # the one host sync
         M, P = total >> 32, total & 0xFFFFFFFF
         with _stage(state, "bin_sort_gather"):

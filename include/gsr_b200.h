@@ -178,14 +178,18 @@ int gsr_render_depth(int N, const float* xyz_camera_frame, const float* uvs, con
 size_t gsr_preprocess_temp_bytes(int N);
 /* inputs: xyz [N,3], quaternion [N,4], scale [N,3], opacity_logit [N], rgb_dc [N,3],
  *         sh_rest [N,3,n_sh_rest] (n_sh_rest in {0,3,8,15}; may be NULL when 0),
- *         camera_T_world [4,4] and K [3,3] ON DEVICE.
+ *         camera_T_world [4,4] and K [3,3] ON DEVICE;
+ *         xyz_camera_frame [N,3] or NULL: camera-frame positions computed by the caller (the reference
+ *         forms them with torch.matmul, whose rounding order belongs to cuBLAS); when NULL the kernel
+ *         applies camera_T_world itself (FMA chain in k order).
  * outputs (all indexed by ORIGINAL gaussian index):
  *   records  float [N,12]   packed splat record (undefined for culled rows)
  *   depth_key uint32 [N]    order-preserving key of camera-frame z
  *   visible  uint8 [N]      1 = survives the frustum cull (culling_mask = !visible)
  *   scan     uint64 [N]     INCLUSIVE scan of (visible << 32 | tiles_touched);
  *                           scan[N-1] >> 32 == M, scan[N-1] & 0xffffffff == P */
-int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
+int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* xyz_camera_frame,
+                           const float* quaternion,
                            const float* scale, const float* opacity_logit, const float* rgb_dc,
                            const float* sh_rest, const float* camera_T_world, const float* K, int H,
                            int W, float near_thresh, float far_thresh, float cull_mask_padding,

@@ -125,8 +125,8 @@ def main():
     # B/C. synthetic scenes: tiny (SH3, 2000 gaussians, 64x64) and small (SH3, 20000 gaussians, 320x192,
     #      fat splats: > 960 splats in some tiles, saturated pixels)
     for name, nG, res, sig, sh_deg in (("synth_tiny", 2000, "tiny", (2.0, 0.5, 0.5, 8.0), 3),
-                                       ("synth_small", 20000, "small", SMALL_SIGMA, 3),
-                                       ("synth_small_nosh", 20000, "small", SMALL_SIGMA, 0)):
+                                       ("synth_small", 12000, "small", SMALL_SIGMA, 3),
+                                       ("synth_deep_nosh", 60000, "small", SMALL_SIGMA, 0)):
         sc = scenes.np_scene(nG, res, sh_degree=sh_deg, seed=0, view=0, n_views=3, sigma_px=sig)
         G = synth.make_upstream_grad(res).numpy()
         st = stages(ref_ext, sc, dev)
@@ -137,11 +137,16 @@ def main():
         keepers = dict(r)
         if "g_sh" in keepers and nG > 4000:
             keepers["g_sh_rows8"] = keepers.pop("g_sh")[::8].copy()
+        if nG > 30000:  # keep the deep fixture small: every 8th gaussian's gradients
+            for k in [k for k in keepers if k.startswith("g_") and k != "g_uv"]:
+                keepers[k + "_rows8"] = keepers.pop(k)[::8].copy()
+            keepers["g_uv_rows8"] = keepers.pop("g_uv")[::8].copy()
         cnt = st["tile_ranges"][1:] - st["tile_ranges"][:-1]
         np.savez_compressed(out / f"{name}_fp32.npz", **keepers, **rs,
-                            st_uv_all=st["uv_all"], st_conic_all=st["conic_all"], st_sorted_idx=st["sorted_idx"],
-                            st_tile_ranges=st["tile_ranges"], st_render_rgb=st["render_rgb"],
-                            st_opacity_act=st["opacity_act"], st_xyz_cam=st["xyz_cam"],
+                            **({} if nG > 30000 else dict(
+                                st_uv_all=st["uv_all"], st_conic_all=st["conic_all"], st_render_rgb=st["render_rgb"],
+                                st_opacity_act=st["opacity_act"], st_xyz_cam=st["xyz_cam"])),
+                            st_sorted_idx=st["sorted_idx"], st_tile_ranges=st["tile_ranges"],
                             ref_noise=np.array([noise[k] for k in sorted(noise)]), ref_noise_keys=np.array(sorted(noise)),
                             max_splats_per_tile=int(cnt.max()))
         meta[name] = dict(P=int(st["sorted_idx"].size), max_splats_per_tile=int(cnt.max()), M=int((~r["culling_mask"]).sum()),

@@ -146,6 +146,12 @@ def main():
             cand.setdefault("E_pairwise", []).append(f32(fma(x, t0, f32(y * t1)) + fma(z, t2, t3)))
         out["transform_order_match_fraction"] = {
             k: float((torch.stack(v, 1).float() == xyz_cam).float().mean()) for k, v in cand.items()}
+        import numpy as _np
+        Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+        _np.savez(str(Path(args.out).with_suffix("")) + "_transform_sample.npz", xyz=g.xyz[:20000].cpu().numpy(),
+                  T=T.cpu().numpy(), xyz_cam=xyz_cam[:20000].cpu().numpy())
+        if not args.no_timing:
+            out["t_transform_points_torch"] = timed(lambda: ref_utils.transform_points_torch(g.xyz, T))
         uv_ref = torch.zeros(args.n, 2, device=dev)
         ref_ext.camera_projection_cuda(xyz_cam, cam.K, uv_ref)
         uv_b = torch.zeros(args.n, 2, device=dev)
@@ -184,7 +190,7 @@ def main():
         out = {}
         sh = g.sh
         rec, zkey, vis, scan = ext.fused_preprocess_forward(
-            g.xyz, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, sh, T, cam.K, H, W,
+            g.xyz, None, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, sh, T, cam.K, H, W,
             cfg["near_thresh"], cfg["far_thresh"], cfg["cull_mask_padding"], cfg["mh_dist"])
         xyz_cam = state["xyz_cam"]
         uv = state["uv"]
