@@ -27,9 +27,12 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--module", default=None, help="run one test module in-process (used by the driver mode)")
     ap.add_argument("--per-module-timeout", type=int, default=120)
+    ap.add_argument("--modules", default=None, help="comma-separated subset of test modules")
     args = ap.parse_args()
     names = ["test_projection", "test_tile_culling", "test_rasterize", "test_depth", "test_structs", "test_utils",
              "test_cuda_autograd_functions", "test_rasterize_autograd"]
+    if args.modules:
+        names = args.modules.split(",")
     if args.module is None:
         # driver mode: one subprocess per module, each with its own timeout, so a hang is isolated and named
         import subprocess
