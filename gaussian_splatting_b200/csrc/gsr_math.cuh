@@ -47,18 +47,19 @@ template <> struct Ar<double> {
 };
 
 // ---------------------------------------------------------------------------
-// world -> camera.  Reference: splat_py/utils.py:60-72 (torch.matmul of the
-// 4x4 with [x,y,z,1]); rounding order = k-ascending FMA chain from a zero
-// accumulator (what the cuBLAS sgemm kernel torch dispatches to executes for
-// K=4; confirmed against torch on B200 by tests/test_parity_gpu.py).
+// world -> camera.  Reference: splat_py/utils.py:60-72, i.e. torch.matmul of the
+// 4x4 with [x,y,z,1], which torch runs as a batched 4x4 @ 4x1 product in cuBLAS.
+// The rounding order of that kernel (identified by exhaustive search over
+// evaluation trees against torch's output on B200, tools/parity_report.py):
+// four separately rounded products reduced pairwise, (p0 + p1) + (p2 + p3).
 // ---------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void transform_point(const T* __restrict__ M /*4x4 row-major*/,
                                                 T x, T y, T z, T& ox, T& oy, T& oz) {
     using A = Ar<T>;
-    ox = A::add(A::fma(z, M[2], A::fma(y, M[1], A::mul(x, M[0]))), M[3]);
-    oy = A::add(A::fma(z, M[6], A::fma(y, M[5], A::mul(x, M[4]))), M[7]);
-    oz = A::add(A::fma(z, M[10], A::fma(y, M[9], A::mul(x, M[8]))), M[11]);
+    ox = A::add(A::add(A::mul(x, M[0]), A::mul(y, M[1])), A::add(A::mul(z, M[2]), M[3]));
+    oy = A::add(A::add(A::mul(x, M[4]), A::mul(y, M[5])), A::add(A::mul(z, M[6]), M[7]));
+    oz = A::add(A::add(A::mul(x, M[8]), A::mul(y, M[9])), A::add(A::mul(z, M[10]), M[11]));
 }
 
 // ---------------------------------------------------------------------------

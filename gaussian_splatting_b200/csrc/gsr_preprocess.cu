@@ -60,11 +60,15 @@ __device__ void camera_centre(const float* __restrict__ T, float* __restrict__ c
 }
 
 __device__ __forceinline__ void load_view(const float* __restrict__ T, const float* __restrict__ K,
-                                          ViewConsts& vc) {
+                                          const float* __restrict__ cam, ViewConsts& vc) {
     // called by one thread per block, result lives in shared memory
     for (int k = 0; k < 16; ++k) vc.T[k] = T[k];
     for (int k = 0; k < 9; ++k) vc.K[k] = K[k];
-    camera_centre(vc.T, vc.cam);
+    if (cam != nullptr) {
+        vc.cam[0] = cam[0]; vc.cam[1] = cam[1]; vc.cam[2] = cam[2];
+    } else {
+        camera_centre(vc.T, vc.cam);
+    }
 }
 
 // SH -> RGB exactly as src/precompute_sh.cu:29-56 evaluates it on cat(rgb_dc, sh_rest)
@@ -94,12 +98,13 @@ __global__ void __launch_bounds__(PRE_THREADS)
                      const float* __restrict__ quat,
                      const float* __restrict__ scale, const float* __restrict__ opa_logit,
                      const float* __restrict__ rgb_dc, const float* __restrict__ sh_rest,
-                     const float* __restrict__ Tdev, const float* __restrict__ Kdev, float width,
-                     float height, float near_t, float far_t, float pad, float mh, int ntx, int nty,
+                     const float* __restrict__ Tdev, const float* __restrict__ Kdev,
+                     const float* __restrict__ camdev, float width, float height, float near_t, float far_t,
+                     float pad, float mh, int ntx, int nty,
                      float* __restrict__ records, uint32_t* __restrict__ zkey,
                      uint8_t* __restrict__ visible, uint64_t* __restrict__ packed) {
     __shared__ ViewConsts vc;
-    if (threadIdx.x == 0) load_view(Tdev, Kdev, vc);
+    if (threadIdx.x == 0) load_view(Tdev, Kdev, camdev, vc);
     __syncthreads();
     const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
     if (i >= N) return;
@@ -177,13 +182,14 @@ __global__ void __launch_bounds__(PRE_THREADS)
     k_preprocess_bwd(int N, const float* __restrict__ xyz, const float* __restrict__ quat,
                      const float* __restrict__ scale, const float* __restrict__ opa_logit,
                      const float* __restrict__ Tdev, const float* __restrict__ Kdev,
-                     const uint8_t* __restrict__ visible, const float* __restrict__ g_rgb,
+                     const float* __restrict__ camdev, const uint8_t* __restrict__ visible,
+                     const float* __restrict__ g_rgb,
                      const float* __restrict__ g_opa, const float* __restrict__ g_uv,
                      const float* __restrict__ g_conic, float* __restrict__ o_xyz,
                      float* __restrict__ o_quat, float* __restrict__ o_scale, float* __restrict__ o_opa,
                      float* __restrict__ o_dc, float* __restrict__ o_sh) {
     __shared__ ViewConsts vc;
-    if (threadIdx.x == 0) load_view(Tdev, Kdev, vc);
+    if (threadIdx.x == 0) load_view(Tdev, Kdev, camdev, vc);
     __syncthreads();
     const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
     if (i >= N) return;
@@ -270,10 +276,10 @@ size_t gsr_preprocess_temp_bytes(int N) {
 int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* xyz_camera_frame,
                            const float* quaternion,
                            const float* scale, const float* opacity_logit, const float* rgb_dc,
-                           const float* sh_rest, const float* camera_T_world, const float* K, int H,
-                           int W, float near_thresh, float far_thresh, float cull_mask_padding,
-                           float mh_dist, float* records, uint32_t* depth_key, uint8_t* visible,
-                           uint64_t* scan, void* temp, size_t temp_bytes, void* stream) {
+                           const float* sh_rest, const float* camera_T_world, const float* K,
+                           const float* camera_centre, int H, int W, float near_thresh, float far_thresh,
+                           float cull_mask_padding, float mh_dist, float* records, uint32_t* depth_key,
+                           uint8_t* visible, uint64_t* scan, void* temp, size_t temp_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
     if (temp_bytes < gsr_preprocess_temp_bytes(N)) return GSR_ERR_BAD_ARG;
@@ -283,8 +289,8 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
     const int ntx = (W + TILE - 1) / TILE, nty = (H + TILE - 1) / TILE;
     const dim3 grid((N + PRE_THREADS - 1) / PRE_THREADS), block(PRE_THREADS);
 #define GSR_PRE_ARGS                                                                              \
-    N, xyz, xyz_camera_frame, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K, (float)W, \
-        (float)H,                                                                                          \
+    N, xyz, xyz_camera_frame, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K,          \
+        camera_centre, (float)W, (float)H,                                                                 \
         near_thresh, far_thresh, cull_mask_padding, mh_dist, ntx, nty, records, depth_key, visible, packed
     switch (n_sh_rest) {
         case 0: k_preprocess_fwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
@@ -301,7 +307,8 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
 
 int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
                             const float* scale, const float* opacity_logit, const float* camera_T_world,
-                            const float* K, const uint8_t* visible, const float* grad_rgb,
+                            const float* K, const float* camera_centre, const uint8_t* visible,
+                            const float* grad_rgb,
                             const float* grad_opacity, const float* grad_uv, const float* grad_conic,
                             float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
                             float* g_rgb_dc, float* g_sh_rest, void* stream) {
@@ -309,7 +316,8 @@ int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float*
     if (N <= 0) return GSR_OK;
     const dim3 grid((N + PRE_THREADS - 1) / PRE_THREADS), block(PRE_THREADS);
 #define GSR_PRE_ARGS                                                                                   \
-    N, xyz, quaternion, scale, opacity_logit, camera_T_world, K, visible, grad_rgb, grad_opacity, grad_uv, \
+    N, xyz, quaternion, scale, opacity_logit, camera_T_world, K, camera_centre, visible, grad_rgb,         \
+        grad_opacity, grad_uv,                                                                             \
         grad_conic, g_xyz, g_quaternion, g_scale, g_opacity_logit, g_rgb_dc, g_sh_rest
     switch (n_sh_rest) {
         case 0: k_preprocess_bwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;

@@ -411,8 +411,8 @@ void render_depth_cuda(torch::Tensor xyz_camera_frame, torch::Tensor uvs, torch:
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_preprocess_forward(
     torch::Tensor xyz, c10::optional<torch::Tensor> xyz_camera_frame, torch::Tensor quaternion, torch::Tensor scale,
     torch::Tensor opacity_logit, torch::Tensor rgb_dc, c10::optional<torch::Tensor> sh_rest,
-    torch::Tensor camera_T_world, torch::Tensor K, int64_t H, int64_t W, double near_thresh, double far_thresh,
-    double cull_mask_padding, double mh_dist) {
+    torch::Tensor camera_T_world, torch::Tensor K, c10::optional<torch::Tensor> camera_centre, int64_t H, int64_t W,
+    double near_thresh, double far_thresh, double cull_mask_padding, double mh_dist) {
     CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(quaternion); CHECK_VALID_INPUT(scale); CHECK_VALID_INPUT(opacity_logit);
     CHECK_VALID_INPUT(rgb_dc); CHECK_VALID_INPUT(camera_T_world); CHECK_VALID_INPUT(K);
     CHECK_FLOAT_TENSOR(xyz); CHECK_FLOAT_TENSOR(quaternion); CHECK_FLOAT_TENSOR(scale);
@@ -431,6 +431,12 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
         CHECK_VALID_INPUT(pc); CHECK_FLOAT_TENSOR(pc);
         TORCH_CHECK(pc.dim() == 2 && pc.size(0) == N && pc.size(1) == 3, "xyz_camera_frame must have shape Nx3");
         cam_ptr = pc.data_ptr<float>();
+    }
+    const float* centre_ptr = nullptr;
+    if (camera_centre.has_value()) {
+        CHECK_VALID_INPUT((*camera_centre)); CHECK_FLOAT_TENSOR((*camera_centre));
+        TORCH_CHECK(camera_centre->numel() == 3, "camera_centre must have 3 elements");
+        centre_ptr = camera_centre->data_ptr<float>();
     }
     int n_rest = 0;
     const float* sh_ptr = nullptr;
@@ -452,7 +458,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
     torch::Tensor temp = torch::empty({(int64_t)tb}, opt.dtype(torch::kUInt8));
     check_rc(gsr_preprocess_forward(N, n_rest, F32PTR(xyz), cam_ptr, F32PTR(quaternion), F32PTR(scale),
                                     F32PTR(opacity_logit), F32PTR(rgb_dc), sh_ptr, F32PTR(camera_T_world),
-                                    F32PTR(K), (int)H, (int)W, (float)near_thresh, (float)far_thresh,
+                                    F32PTR(K), centre_ptr, (int)H, (int)W, (float)near_thresh, (float)far_thresh,
                                     (float)cull_mask_padding, (float)mh_dist, F32PTR(records),
                                     (uint32_t*)zkey.data_ptr<int>(), visible.data_ptr<uint8_t>(),
                                     (uint64_t*)scan.data_ptr<int64_t>(), temp.data_ptr(), tb, cur_stream()),
@@ -544,6 +550,7 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
                                                      torch::Tensor opacity_logit,
                                                      c10::optional<torch::Tensor> sh_rest,
                                                      torch::Tensor camera_T_world, torch::Tensor K,
+                                                     c10::optional<torch::Tensor> camera_centre,
                                                      torch::Tensor visible) {
     CHECK_VALID_INPUT(slab); CHECK_FLOAT_TENSOR(slab);
     const int64_t N = xyz.size(0);
@@ -565,6 +572,7 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
                   o_dc = torch::empty({N, 3}, opt);
     check_rc(gsr_preprocess_backward((int)N, n_rest, F32PTR(xyz), F32PTR(quaternion), F32PTR(scale),
                                      F32PTR(opacity_logit), F32PTR(camera_T_world), F32PTR(K),
+                                     camera_centre.has_value() ? camera_centre->data_ptr<float>() : nullptr,
                                      visible.data_ptr<uint8_t>(), g_rgb, g_opa, g_uv, g_conic, F32PTR(o_xyz),
                                      F32PTR(o_q), F32PTR(o_s), F32PTR(o_o), F32PTR(o_dc),
                                      n_rest ? F32PTR(g_sh) : nullptr, cur_stream()),

@@ -36,7 +36,7 @@ from .tile_culling import get_splats
 from .utils import compute_rays_in_world_frame, transform_points_torch
 
 
-IN_KERNEL_TRANSFORM = False
+IN_KERNEL_TRANSFORM = True
 
 
 class _ViewState:
@@ -78,9 +78,15 @@ class _ProjectGaussians(torch.autograd.Function):
         # splat_py/utils.py:60-72), because their bits decide tile membership and the 1/255 skip and the
         # rounding order inside cuBLAS is not ours to pin; IN_KERNEL_TRANSFORM folds it into the kernel.
         xyz_cam = None if IN_KERNEL_TRANSFORM else transform_points_torch(xyz, camera_T_world)
+        # camera centre for the SH view direction: same LU-based inverse as the reference's torch.inverse
+        # (splat_py/rasterize.py:91-93), through inv_ex so that no host sync is involved
+        centre = None
+        if sh is not None:
+            centre = torch.linalg.inv_ex(camera_T_world)[0][:3, 3].contiguous()
         with _stage(state, "preprocess_fwd"):
             records, zkey, visible, scan = ext.fused_preprocess_forward(
-                xyz, xyz_cam, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, H, W, near, far, pad, mh)
+                xyz, xyz_cam, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, centre, H, W, near, far,
+                pad, mh)
         total = int(scan[-1].item()) if xyz.shape[0] > 0 else 0  # the one host sync
         M, P = total >> 32, total & 0xFFFFFFFF
         with _stage(state, "bin_sort_gather"):
@@ -91,12 +97,12 @@ class _ProjectGaussians(torch.autograd.Function):
         carrier = torch.empty(9 * xyz.shape[0], dtype=xyz.dtype, device=xyz.device)
         ctx.state = state
         ctx.has_sh = sh is not None
-        ctx.save_for_backward(xyz, quaternion, scale, opacity_flat, sh, camera_T_world, K)
+        ctx.save_for_backward(xyz, quaternion, scale, opacity_flat, sh, camera_T_world, K, centre)
         return uv, carrier
 
     @staticmethod
     def backward(ctx, grad_uv, grad_carrier):
-        xyz, quaternion, scale, opacity_flat, sh, camera_T_world, K = ctx.saved_tensors
+        xyz, quaternion, scale, opacity_flat, sh, camera_T_world, K, centre = ctx.saved_tensors
         st = ctx.state
         N = st.N
         if grad_carrier is None:
@@ -108,7 +114,7 @@ class _ProjectGaussians(torch.autograd.Function):
             slab[4 * N:6 * N].view(N, 2).index_copy_(0, st.vis_idx, grad_uv.contiguous())
         with _stage(st, "preprocess_bwd"):
             grads = native().fused_preprocess_backward(slab, xyz, quaternion, scale, opacity_flat, sh,
-                                                       camera_T_world, K, st.visible)
+                                                       camera_T_world, K, centre, st.visible)
         g_xyz, g_q, g_s, g_o, g_dc = grads[:5]
         g_sh = grads[5] if ctx.has_sh else None
         return g_xyz, g_q, g_s, g_o.view(-1, 1), g_dc, g_sh, None, None, None, None

@@ -181,7 +181,9 @@ size_t gsr_preprocess_temp_bytes(int N);
  *         camera_T_world [4,4] and K [3,3] ON DEVICE;
  *         xyz_camera_frame [N,3] or NULL: camera-frame positions computed by the caller (the reference
  *         forms them with torch.matmul, whose rounding order belongs to cuBLAS); when NULL the kernel
- *         applies camera_T_world itself (FMA chain in k order).
+ *         applies camera_T_world itself with the same rounding order;
+ *         camera_centre [3] or NULL: inverse(camera_T_world)[:3,3] computed by the caller (the reference
+ *         uses torch.inverse); when NULL the kernel inverts the pose itself (fp64 Gauss-Jordan).
  * outputs (all indexed by ORIGINAL gaussian index):
  *   records  float [N,12]   packed splat record (undefined for culled rows)
  *   depth_key uint32 [N]    order-preserving key of camera-frame z
@@ -191,10 +193,10 @@ size_t gsr_preprocess_temp_bytes(int N);
 int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* xyz_camera_frame,
                            const float* quaternion,
                            const float* scale, const float* opacity_logit, const float* rgb_dc,
-                           const float* sh_rest, const float* camera_T_world, const float* K, int H,
-                           int W, float near_thresh, float far_thresh, float cull_mask_padding,
-                           float mh_dist, float* records, uint32_t* depth_key, uint8_t* visible,
-                           uint64_t* scan, void* temp, size_t temp_bytes, void* stream);
+                           const float* sh_rest, const float* camera_T_world, const float* K,
+                           const float* camera_centre, int H, int W, float near_thresh, float far_thresh,
+                           float cull_mask_padding, float mh_dist, float* records, uint32_t* depth_key,
+                           uint8_t* visible, uint64_t* scan, void* temp, size_t temp_bytes, void* stream);
 
 /* emits the (tile, depth) keys and original-gaussian ids of all P pairs, the compact list of
  * visible gaussian ids vis_idx int32 [M] and the compacted uv [M,2] the reference returns */
@@ -219,7 +221,7 @@ int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, 
  * parameter gradients for all N gaussians (zeros for culled ones). */
 int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
                             const float* scale, const float* opacity_logit, const float* camera_T_world,
-                            const float* K, const uint8_t* visible, const float* grad_rgb,
+                            const float* K, const float* camera_centre, const uint8_t* visible, const float* grad_rgb,
                             const float* grad_opacity, const float* grad_uv, const float* grad_conic,
                             float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
                             float* g_rgb_dc, float* g_sh_rest, void* stream);

@@ -190,7 +190,7 @@ def main():
         out = {}
         sh = g.sh
         rec, zkey, vis, scan = ext.fused_preprocess_forward(
-            g.xyz, None, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, sh, T, cam.K, H, W,
+            g.xyz, None, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, sh, T, cam.K, None, H, W,
             cfg["near_thresh"], cfg["far_thresh"], cfg["cull_mask_padding"], cfg["mh_dist"])
         xyz_cam = state["xyz_cam"]
         uv = state["uv"]
