@@ -48,18 +48,21 @@ template <> struct Ar<double> {
 
 // ---------------------------------------------------------------------------
 // world -> camera.  Reference: splat_py/utils.py:60-72, i.e. torch.matmul of the
-// 4x4 with [x,y,z,1], which torch runs as a batched 4x4 @ 4x1 product in cuBLAS.
-// The rounding order of that kernel (identified by exhaustive search over
-// evaluation trees against torch's output on B200, tools/parity_report.py):
-// four separately rounded products reduced pairwise, (p0 + p1) + (p2 + p3).
+// 4x4 with [x,y,z,1], which torch runs as a batched (4x4)@(4x1) product in cuBLAS.
+// The rounding order of the cuBLAS kernel used for large batches (>= 2000 points on
+// this image's cuBLAS 12.8; identified by exhaustive search over evaluation trees
+// against torch's output on B200, tools/check_transform.py) is a 2-way split over k:
+//     (x*m0 -> fma(y, m1, .))  +  (z*m2 -> fma(1, m3, .))
+// Small batches go through a different cuBLAS kernel; the host mirror hands those to
+// torch itself (gaussian_splatting_b200/rasterize.py) so the bits always match.
 // ---------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void transform_point(const T* __restrict__ M /*4x4 row-major*/,
                                                 T x, T y, T z, T& ox, T& oy, T& oz) {
     using A = Ar<T>;
-    ox = A::add(A::add(A::mul(x, M[0]), A::mul(y, M[1])), A::add(A::mul(z, M[2]), M[3]));
-    oy = A::add(A::add(A::mul(x, M[4]), A::mul(y, M[5])), A::add(A::mul(z, M[6]), M[7]));
-    oz = A::add(A::add(A::mul(x, M[8]), A::mul(y, M[9])), A::add(A::mul(z, M[10]), M[11]));
+    ox = A::add(A::fma(y, M[1], A::mul(x, M[0])), A::add(A::mul(z, M[2]), M[3]));
+    oy = A::add(A::fma(y, M[5], A::mul(x, M[4])), A::add(A::mul(z, M[6]), M[7]));
+    oz = A::add(A::fma(y, M[9], A::mul(x, M[8])), A::add(A::mul(z, M[10]), M[11]));
 }
 
 // ---------------------------------------------------------------------------

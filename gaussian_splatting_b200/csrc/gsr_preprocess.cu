@@ -22,7 +22,8 @@
 
 namespace gsr {
 
-constexpr int PRE_THREADS = 256;
+constexpr int PRE_THREADS = 128;  // gaussians per CTA; every per-gaussian array slice of a CTA is one contiguous,
+                                  // 16-byte aligned run in HBM, moved by TMA bulk copies
 
 struct ViewConsts {
     float T[16];
@@ -60,13 +61,13 @@ __device__ void camera_centre(const float* __restrict__ T, float* __restrict__ c
 }
 
 __device__ __forceinline__ void load_view(const float* __restrict__ T, const float* __restrict__ K,
-                                          const float* __restrict__ cam, ViewConsts& vc) {
+                                          const float* __restrict__ cam, ViewConsts& vc, bool need_centre = true) {
     // called by one thread per block, result lives in shared memory
     for (int k = 0; k < 16; ++k) vc.T[k] = T[k];
     for (int k = 0; k < 9; ++k) vc.K[k] = K[k];
     if (cam != nullptr) {
         vc.cam[0] = cam[0]; vc.cam[1] = cam[1]; vc.cam[2] = cam[2];
-    } else {
+    } else if (need_centre) {
         camera_centre(vc.T, vc.cam);
     }
 }
@@ -92,6 +93,12 @@ __device__ __forceinline__ void sh_rgb_fused(const float* __restrict__ dc, const
     }
 }
 
+// cooperative, coalesced smem <-> global copies for the last (partial) block, where TMA's 16-byte
+// granularity does not hold
+__device__ __forceinline__ void coop_copy(float* __restrict__ dst, const float* __restrict__ src, int n_floats) {
+    for (int k = threadIdx.x; k < n_floats; k += PRE_THREADS) dst[k] = src[k];
+}
+
 template <int N_SH, bool HAS_SH>
 __global__ void __launch_bounds__(PRE_THREADS)
     k_preprocess_fwd(int N, const float* __restrict__ xyz, const float* __restrict__ xyz_cam,
@@ -102,77 +109,107 @@ __global__ void __launch_bounds__(PRE_THREADS)
                      const float* __restrict__ camdev, float width, float height, float near_t, float far_t,
                      float pad, float mh, int ntx, int nty,
                      float* __restrict__ records, uint32_t* __restrict__ zkey,
-                     uint8_t* __restrict__ visible, uint64_t* __restrict__ packed) {
+                     uint8_t* __restrict__ visible, uint64_t* __restrict__ packed, int use_tma) {
+    constexpr int NR3 = HAS_SH ? 3 * (N_SH - 1) : 1;
     __shared__ ViewConsts vc;
-    if (threadIdx.x == 0) load_view(Tdev, Kdev, camdev, vc);
-    __syncthreads();
-    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
-    if (i >= N) return;
-
-    const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
-    float px, py, pz, u, v;
-    if (xyz_cam != nullptr) {
-        px = xyz_cam[i * 3 + 0]; py = xyz_cam[i * 3 + 1]; pz = xyz_cam[i * 3 + 2];
-    } else {
-        transform_point<float>(vc.T, x, y, z, px, py, pz);
-    }
-    project_uv<float>(px, py, pz, vc.K[0], vc.K[2], vc.K[4], vc.K[5], u, v);
-    // splat_py/rasterize.py:38-49 (strict compares, fp32)
-    const bool culled = (pz < near_t) | (pz > far_t) | (u < -pad) | (u > width + pad) | (v < -pad) |
-                        (v > height + pad);
-    zkey[i] = depth_key(pz);
-    // NaN coordinates compare false everywhere and would survive; the reference aborts on them
-    // (splat_py/tile_culling.py:15-18) — treat as culled instead.
-    const bool vis = !culled && (pz == pz) && (u == u) && (v == v);
-    visible[i] = vis ? 1 : 0;
-    if (!vis) {
-        packed[i] = 0ull;
-        return;
-    }
-    float S6[6], S9[9], J[6], W[9], conic[3];
-    sigma_world<float>(quat[i * 4 + 0], quat[i * 4 + 1], quat[i * 4 + 2], quat[i * 4 + 3], scale[i * 3 + 0],
-                       scale[i * 3 + 1], scale[i * 3 + 2], S6);
-    sym6_to_full(S6, S9);
-    proj_jacobian<float>(px, py, pz, vc.K[0], vc.K[4], J);
-    W[0] = vc.T[0]; W[1] = vc.T[1]; W[2] = vc.T[2];
-    W[3] = vc.T[4]; W[4] = vc.T[5]; W[5] = vc.T[6];
-    W[6] = vc.T[8]; W[7] = vc.T[9]; W[8] = vc.T[10];
-    conic_from<float>(S9, J, W, conic, nullptr);
-
-    const float opa = sigmoid_torch(opa_logit[i]);
-    float dc[3] = {rgb_dc[i * 3 + 0], rgb_dc[i * 3 + 1], rgb_dc[i * 3 + 2]};
-    float col[3];
-    if (HAS_SH) {
-        float rest[3 * (N_SH - 1) + 1];
-        const float* src = sh_rest + (size_t)i * 3 * (N_SH - 1);
-#pragma unroll
-        for (int k = 0; k < 3 * (N_SH - 1); ++k) rest[k] = src[k];
-        sh_rgb_fused<N_SH>(dc, rest, x, y, z, vc.cam, col);
-    } else {
-        col[0] = dc[0]; col[1] = dc[1]; col[2] = dc[2];
-    }
-    float rec[REC];
-    make_record(u, v, conic[0], conic[1], conic[2], opa, col[0], col[1], col[2], rec);
-    float4* o = reinterpret_cast<float4*>(records + (size_t)i * REC);
-    o[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-    o[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-    o[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
-
-    // tiles touched (src/tile_culling.cu:139-176)
-    Obb ob;
-    compute_obb(u, v, rec[R_A], __fmul_rn(rec[R_B2], 0.5f), rec[R_C], mh, ob);
-    int x0, x1, y0, y1, cnt = 0;
-    tile_window(u, v, ob.radius_tiles, ntx, nty, x0, x1, y0, y1);
-    for (int tx = x0; tx < x1; ++tx) {
-        const float left = __fmul_rn(__int2float_rn(tx), 16.0f);
-        const float right = __fmul_rn(__int2float_rn(tx + 1), 16.0f);
-        for (int ty = y0; ty < y1; ++ty) {
-            const float top = __fmul_rn(__int2float_rn(ty), 16.0f);
-            const float bottom = __fmul_rn(__int2float_rn(ty + 1), 16.0f);
-            cnt += obb_hits_tile(ob, left, right, top, bottom) ? 1 : 0;
+    __shared__ __align__(128) float s_sh[PRE_THREADS * NR3];       // SH coefficients of the CTA's gaussians
+    __shared__ __align__(128) float s_rec[PRE_THREADS * REC];      // output records
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.x * PRE_THREADS;
+    const int cnt = min(PRE_THREADS, N - i0);
+    const bool tma = use_tma && cnt == PRE_THREADS;
+    if (tid == 0) {
+        load_view(Tdev, Kdev, camdev, vc, HAS_SH);
+        if (HAS_SH && tma) {
+            mbar_init(&s_bar, 1);
+            fence_mbar_init();
+            const uint32_t bytes = (uint32_t)(PRE_THREADS * NR3 * sizeof(float));
+            mbar_arrive_expect_tx(&s_bar, bytes);
+            tma_load_1d(s_sh, sh_rest + (size_t)i0 * NR3, bytes, &s_bar);
         }
     }
-    packed[i] = (1ull << 32) | (uint64_t)(uint32_t)cnt;
+    if (HAS_SH && !tma) coop_copy(s_sh, sh_rest + (size_t)i0 * NR3, cnt * NR3);
+    __syncthreads();
+    const int i = i0 + tid;
+    float rec[REC];
+#pragma unroll
+    for (int k = 0; k < REC; ++k) rec[k] = 0.0f;
+    if (i < N) {
+        const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
+        float px, py, pz, u, v;
+        if (xyz_cam != nullptr) {
+            px = xyz_cam[i * 3 + 0]; py = xyz_cam[i * 3 + 1]; pz = xyz_cam[i * 3 + 2];
+        } else {
+            transform_point<float>(vc.T, x, y, z, px, py, pz);
+        }
+        project_uv<float>(px, py, pz, vc.K[0], vc.K[2], vc.K[4], vc.K[5], u, v);
+        // splat_py/rasterize.py:38-49 (strict compares, fp32)
+        const bool culled = (pz < near_t) | (pz > far_t) | (u < -pad) | (u > width + pad) | (v < -pad) |
+                            (v > height + pad);
+        zkey[i] = depth_key(pz);
+        // NaN coordinates compare false everywhere and would survive; the reference aborts on them
+        // (splat_py/tile_culling.py:15-18) — treat as culled instead.
+        const bool vis = !culled && (pz == pz) && (u == u) && (v == v);
+        visible[i] = vis ? 1 : 0;
+        uint64_t pk = 0ull;
+        if (vis) {
+            float S6[6], S9[9], J[6], W[9], conic[3];
+            sigma_world<float>(quat[i * 4 + 0], quat[i * 4 + 1], quat[i * 4 + 2], quat[i * 4 + 3],
+                               scale[i * 3 + 0], scale[i * 3 + 1], scale[i * 3 + 2], S6);
+            sym6_to_full(S6, S9);
+            proj_jacobian<float>(px, py, pz, vc.K[0], vc.K[4], J);
+            W[0] = vc.T[0]; W[1] = vc.T[1]; W[2] = vc.T[2];
+            W[3] = vc.T[4]; W[4] = vc.T[5]; W[5] = vc.T[6];
+            W[6] = vc.T[8]; W[7] = vc.T[9]; W[8] = vc.T[10];
+            conic_from<float>(S9, J, W, conic, nullptr);
+
+            const float opa = sigmoid_torch(opa_logit[i]);
+            float dc[3] = {rgb_dc[i * 3 + 0], rgb_dc[i * 3 + 1], rgb_dc[i * 3 + 2]};
+            float col[3];
+            if (HAS_SH) {
+                if (tma) mbar_wait(&s_bar, 0);
+                sh_rgb_fused<N_SH>(dc, s_sh + tid * NR3, x, y, z, vc.cam, col);  // stride 3*(N_SH-1): odd, no conflicts
+            } else {
+                col[0] = dc[0]; col[1] = dc[1]; col[2] = dc[2];
+            }
+            make_record(u, v, conic[0], conic[1], conic[2], opa, col[0], col[1], col[2], rec);
+
+            // tiles touched (src/tile_culling.cu:139-176)
+            Obb ob;
+            compute_obb(u, v, rec[R_A], __fmul_rn(rec[R_B2], 0.5f), rec[R_C], mh, ob);
+            int x0, x1, y0, y1, c = 0;
+            tile_window(u, v, ob.radius_tiles, ntx, nty, x0, x1, y0, y1);
+            for (int tx = x0; tx < x1; ++tx) {
+                const float left = __fmul_rn(__int2float_rn(tx), 16.0f);
+                const float right = __fmul_rn(__int2float_rn(tx + 1), 16.0f);
+                for (int ty = y0; ty < y1; ++ty) {
+                    const float top = __fmul_rn(__int2float_rn(ty), 16.0f);
+                    const float bottom = __fmul_rn(__int2float_rn(ty + 1), 16.0f);
+                    c += obb_hits_tile(ob, left, right, top, bottom) ? 1 : 0;
+                }
+            }
+            pk = (1ull << 32) | (uint64_t)(uint32_t)c;
+        }
+        packed[i] = pk;
+    }
+    // records leave through shared memory: one 6 KB bulk store per CTA instead of 48-byte strided stores
+    float4* sr = reinterpret_cast<float4*>(s_rec + tid * REC);
+    sr[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+    sr[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+    sr[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+    if (tma) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_1d(records + (size_t)i0 * REC, s_rec, (uint32_t)(PRE_THREADS * REC * sizeof(float)));
+            tma_store_commit_and_wait();
+        }
+    } else {
+        __syncthreads();
+        coop_copy(records + (size_t)i0 * REC, s_rec, cnt * REC);
+    }
+    if (HAS_SH && tma && tid == 0) mbar_wait(&s_bar, 0);  // never exit with the SH load still in flight
 }
 
 // Fused VJP.  g_rgb/g_opa/g_uv/g_conic are the per-Gaussian sums produced by the render backward
@@ -187,77 +224,106 @@ __global__ void __launch_bounds__(PRE_THREADS)
                      const float* __restrict__ g_opa, const float* __restrict__ g_uv,
                      const float* __restrict__ g_conic, float* __restrict__ o_xyz,
                      float* __restrict__ o_quat, float* __restrict__ o_scale, float* __restrict__ o_opa,
-                     float* __restrict__ o_dc, float* __restrict__ o_sh) {
-    __shared__ ViewConsts vc;
-    if (threadIdx.x == 0) load_view(Tdev, Kdev, camdev, vc);
-    __syncthreads();
-    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
-    if (i >= N) return;
+                     float* __restrict__ o_dc, float* __restrict__ o_sh, int use_tma) {
     constexpr int NR = N_SH - 1;
-    if (!visible[i]) {
+    constexpr int NR3 = HAS_SH ? 3 * NR : 1;
+    // all outputs of the CTA's 128 gaussians are staged in shared memory and leave as six bulk stores
+    __shared__ ViewConsts vc;
+    __shared__ __align__(128) float s_sh[PRE_THREADS * NR3];
+    __shared__ __align__(128) float s_xyz[PRE_THREADS * 3];
+    __shared__ __align__(128) float s_quat[PRE_THREADS * 4];
+    __shared__ __align__(128) float s_scale[PRE_THREADS * 3];
+    __shared__ __align__(128) float s_opa[PRE_THREADS];
+    __shared__ __align__(128) float s_dc[PRE_THREADS * 3];
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.x * PRE_THREADS;
+    const int cnt = min(PRE_THREADS, N - i0);
+    const bool tma = use_tma && cnt == PRE_THREADS;
+    if (tid == 0) load_view(Tdev, Kdev, camdev, vc, HAS_SH);
+    __syncthreads();
+    const int i = i0 + tid;
+    float gx[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, go = 0.f,
+          gdc[3] = {0.f, 0.f, 0.f};
+    float* my_sh = s_sh + tid * NR3;
+    bool vis = false;
+    if (i < N) vis = visible[i] != 0;
+    if (vis) {
+        const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
+        float px, py, pz;
+        transform_point<float>(vc.T, x, y, z, px, py, pz);
+        const float qw = quat[i * 4 + 0], qx = quat[i * 4 + 1], qy = quat[i * 4 + 2], qz = quat[i * 4 + 3];
+        const float s0 = scale[i * 3 + 0], s1 = scale[i * 3 + 1], s2 = scale[i * 3 + 2];
+        float S6[6], S9[9], J[6], W[9];
+        sigma_world<float>(qw, qx, qy, qz, s0, s1, s2, S6);
+        sym6_to_full(S6, S9);
+        proj_jacobian<float>(px, py, pz, vc.K[0], vc.K[4], J);
+        W[0] = vc.T[0]; W[1] = vc.T[1]; W[2] = vc.T[2];
+        W[3] = vc.T[4]; W[4] = vc.T[5]; W[5] = vc.T[6];
+        W[6] = vc.T[8]; W[7] = vc.T[9]; W[8] = vc.T[10];
+
+        const float gc[3] = {g_conic[i * 3 + 0], g_conic[i * 3 + 1], g_conic[i * 3 + 2]};
+        float gS[9], gJ[6];
+        conic_bwd<float>(S9, J, W, gc, gS, gJ);
+        sigma_world_bwd<float>(qw, qx, qy, qz, s0, s1, s2, gS, gq, gs);
+        float gp_j[3], gp_uv[3] = {0.f, 0.f, 0.f};
+        proj_jacobian_bwd<float>(px, py, pz, vc.K[0], vc.K[4], gJ, gp_j);
+        project_uv_bwd<float>(px, py, pz, vc.K[0], vc.K[4], g_uv[i * 2 + 0], g_uv[i * 2 + 1], gp_uv);
+        const float gp[3] = {gp_j[0] + gp_uv[0], gp_j[1] + gp_uv[1], gp_j[2] + gp_uv[2]};
+        // xyz_cam = W xyz + t  =>  grad_xyz = W^T grad_xyz_cam
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { o_xyz[i * 3 + k] = 0.f; o_scale[i * 3 + k] = 0.f; o_dc[i * 3 + k] = 0.f; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o_quat[i * 4 + k] = 0.f;
-        o_opa[i] = 0.f;
+        for (int k = 0; k < 3; ++k) gx[k] = W[0 + k] * gp[0] + W[3 + k] * gp[1] + W[6 + k] * gp[2];
+        const float sg = sigmoid_torch(opa_logit[i]);
+        go = g_opa[i] * ((1.0f - sg) * sg);  // torch sigmoid_backward: grad * (1 - y) * y
+
+        const float gr[3] = {g_rgb[i * 3 + 0], g_rgb[i * 3 + 1], g_rgb[i * 3 + 2]};
         if (HAS_SH) {
-            float* dst = o_sh + (size_t)i * 3 * NR;
+            // src/precompute_sh.cu:96-109, split into the DC column and the rest
+            float dx, dy, dz, Y[N_SH];
+            view_dir<float>(x, y, z, vc.cam[0], vc.cam[1], vc.cam[2], dx, dy, dz);
+            sh_basis<float, N_SH>(dx, dy, dz, Y);
 #pragma unroll
-            for (int k = 0; k < 3 * NR; ++k) dst[k] = 0.f;
+            for (int c = 0; c < 3; ++c) {
+                const float g = gr[c] * GSR_RSH0;
+                gdc[c] = g * Y[0];
+#pragma unroll
+                for (int k = 1; k < N_SH; ++k) my_sh[c * NR + (k - 1)] = g * Y[k];
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gdc[c] = gr[c];
         }
-        return;
+    } else if (HAS_SH) {
+#pragma unroll
+        for (int k = 0; k < NR3; ++k) my_sh[k] = 0.f;
     }
-    const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
-    float px, py, pz;
-    transform_point<float>(vc.T, x, y, z, px, py, pz);
-    const float qw = quat[i * 4 + 0], qx = quat[i * 4 + 1], qy = quat[i * 4 + 2], qz = quat[i * 4 + 3];
-    const float s0 = scale[i * 3 + 0], s1 = scale[i * 3 + 1], s2 = scale[i * 3 + 2];
-    float S6[6], S9[9], J[6], W[9];
-    sigma_world<float>(qw, qx, qy, qz, s0, s1, s2, S6);
-    sym6_to_full(S6, S9);
-    proj_jacobian<float>(px, py, pz, vc.K[0], vc.K[4], J);
-    W[0] = vc.T[0]; W[1] = vc.T[1]; W[2] = vc.T[2];
-    W[3] = vc.T[4]; W[4] = vc.T[5]; W[5] = vc.T[6];
-    W[6] = vc.T[8]; W[7] = vc.T[9]; W[8] = vc.T[10];
-
-    const float gc[3] = {g_conic[i * 3 + 0], g_conic[i * 3 + 1], g_conic[i * 3 + 2]};
-    float gS[9], gJ[6];
-    conic_bwd<float>(S9, J, W, gc, gS, gJ);
-    float gq[4], gs[3];
-    sigma_world_bwd<float>(qw, qx, qy, qz, s0, s1, s2, gS, gq, gs);
-    float gp_j[3], gp_uv[3] = {0.f, 0.f, 0.f};
-    proj_jacobian_bwd<float>(px, py, pz, vc.K[0], vc.K[4], gJ, gp_j);
-    project_uv_bwd<float>(px, py, pz, vc.K[0], vc.K[4], g_uv[i * 2 + 0], g_uv[i * 2 + 1], gp_uv);
-    const float gp[3] = {gp_j[0] + gp_uv[0], gp_j[1] + gp_uv[1], gp_j[2] + gp_uv[2]};
-    // xyz_cam = W xyz + t  =>  grad_xyz = W^T grad_xyz_cam
 #pragma unroll
-    for (int k = 0; k < 3; ++k) o_xyz[i * 3 + k] = W[0 + k] * gp[0] + W[3 + k] * gp[1] + W[6 + k] * gp[2];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o_quat[i * 4 + k] = gq[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) o_scale[i * 3 + k] = gs[k];
-    const float sg = sigmoid_torch(opa_logit[i]);
-    o_opa[i] = g_opa[i] * ((1.0f - sg) * sg);  // torch sigmoid_backward: grad * (1 - y) * y
-
-    const float gr[3] = {g_rgb[i * 3 + 0], g_rgb[i * 3 + 1], g_rgb[i * 3 + 2]};
-    if (HAS_SH) {
-        // src/precompute_sh.cu:96-109, split into the DC column and the rest
-        float dx, dy, dz, Y[N_SH];
-        view_dir<float>(x, y, z, vc.cam[0], vc.cam[1], vc.cam[2], dx, dy, dz);
-        sh_basis<float, N_SH>(dx, dy, dz, Y);
-        float* dst = o_sh + (size_t)i * 3 * NR;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float g = gr[c] * GSR_RSH0;
-            o_dc[i * 3 + c] = g * Y[0];
-#pragma unroll
-            for (int k = 1; k < N_SH; ++k) dst[c * NR + (k - 1)] = g * Y[k];
+    for (int k = 0; k < 3; ++k) { s_xyz[tid * 3 + k] = gx[k]; s_scale[tid * 3 + k] = gs[k]; s_dc[tid * 3 + k] = gdc[k]; }
+    *reinterpret_cast<float4*>(s_quat + tid * 4) = make_float4(gq[0], gq[1], gq[2], gq[3]);
+    s_opa[tid] = go;
+    if (tma) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_1d(o_xyz + (size_t)i0 * 3, s_xyz, PRE_THREADS * 3 * 4);
+            tma_store_1d(o_quat + (size_t)i0 * 4, s_quat, PRE_THREADS * 4 * 4);
+            tma_store_1d(o_scale + (size_t)i0 * 3, s_scale, PRE_THREADS * 3 * 4);
+            tma_store_1d(o_opa + (size_t)i0, s_opa, PRE_THREADS * 4);
+            tma_store_1d(o_dc + (size_t)i0 * 3, s_dc, PRE_THREADS * 3 * 4);
+            if (HAS_SH) tma_store_1d(o_sh + (size_t)i0 * NR3, s_sh, PRE_THREADS * NR3 * 4);
+            tma_store_commit_and_wait();
         }
     } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) o_dc[i * 3 + c] = gr[c];
+        __syncthreads();
+        coop_copy(o_xyz + (size_t)i0 * 3, s_xyz, cnt * 3);
+        coop_copy(o_quat + (size_t)i0 * 4, s_quat, cnt * 4);
+        coop_copy(o_scale + (size_t)i0 * 3, s_scale, cnt * 3);
+        coop_copy(o_opa + (size_t)i0, s_opa, cnt);
+        coop_copy(o_dc + (size_t)i0 * 3, s_dc, cnt * 3);
+        if (HAS_SH) coop_copy(o_sh + (size_t)i0 * NR3, s_sh, cnt * NR3);
     }
 }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -288,10 +354,11 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
     uint64_t* packed = reinterpret_cast<uint64_t*>((char*)temp + align256(scan_bytes));
     const int ntx = (W + TILE - 1) / TILE, nty = (H + TILE - 1) / TILE;
     const dim3 grid((N + PRE_THREADS - 1) / PRE_THREADS), block(PRE_THREADS);
+    const int use_tma = (aligned16(records) && (sh_rest == nullptr || aligned16(sh_rest))) ? 1 : 0;
 #define GSR_PRE_ARGS                                                                              \
     N, xyz, xyz_camera_frame, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K,          \
         camera_centre, (float)W, (float)H,                                                                 \
-        near_thresh, far_thresh, cull_mask_padding, mh_dist, ntx, nty, records, depth_key, visible, packed
+        near_thresh, far_thresh, cull_mask_padding, mh_dist, ntx, nty, records, depth_key, visible, packed, use_tma
     switch (n_sh_rest) {
         case 0: k_preprocess_fwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
         case 3: k_preprocess_fwd<4, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
@@ -315,10 +382,15 @@ int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float*
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
     const dim3 grid((N + PRE_THREADS - 1) / PRE_THREADS), block(PRE_THREADS);
+    const int use_tma = (aligned16(g_xyz) && aligned16(g_quaternion) && aligned16(g_scale) &&
+                         aligned16(g_opacity_logit) && aligned16(g_rgb_dc) &&
+                         (g_sh_rest == nullptr || aligned16(g_sh_rest)))
+                            ? 1
+                            : 0;
 #define GSR_PRE_ARGS                                                                                   \
     N, xyz, quaternion, scale, opacity_logit, camera_T_world, K, camera_centre, visible, grad_rgb,         \
         grad_opacity, grad_uv,                                                                             \
-        grad_conic, g_xyz, g_quaternion, g_scale, g_opacity_logit, g_rgb_dc, g_sh_rest
+        grad_conic, g_xyz, g_quaternion, g_scale, g_opacity_logit, g_rgb_dc, g_sh_rest, use_tma
     switch (n_sh_rest) {
         case 0: k_preprocess_bwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
         case 3: k_preprocess_bwd<4, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;

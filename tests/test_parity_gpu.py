@@ -392,7 +392,7 @@ def test_full_size_properties():
     for gr in grads1:
         assert bool(torch.isfinite(gr).all())
         assert float(gr[mask].abs().max()) == 0.0
-    assert bool(torch.isfinite(image).all()) and float(image.min()) >= -1e-3
+    assert bool(torch.isfinite(image).all())  # (colours may be negative: SH terms are unclamped, as in the reference)
     # per-pixel walk length never exceeds the tile's list
     cnt = (ranges[1:] - ranges[:-1]).view(68, 120)
     npp = st.n_per_pixel

@@ -39,7 +39,8 @@ def main():
     dev = torch.device("cuda")
     ext = gsb.native()
     rep = {}
-    for n in (6, 100, 2000, 65536, 100000, 1000000, 3000000):
+    Path('gpurun_out').mkdir(exist_ok=True)
+    for n in (6, 100, 1000, 2000, 4096, 16384, 20000, 40000, 65536, 100000, 1000000, 3000000):
         g = synth.make_gaussians(n, "1080p", sh_degree=0, seed=n, device=dev)
         cam = synth.make_camera("1080p", device=dev)
         for name, T in poses(dev).items():
@@ -48,6 +49,9 @@ def main():
                                              cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0)
             b = ext.fused_preprocess_forward(g.xyz, xyz_cam, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, None, T,
                                              cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0)
+            if False:
+                np.savez(f"gpurun_out/transform_sample_N{n}_{name}.npz", xyz=g.xyz[:20000].cpu().numpy(), T=T.cpu().numpy(),
+                         xyz_cam=xyz_cam[:20000].cpu().numpy())
             same_z = float((a[1] == b[1]).float().mean())
             ra, rb = a[0].view(torch.int32), b[0].view(torch.int32)
             fin = torch.isfinite(b[0]).all(dim=1)
