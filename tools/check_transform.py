@@ -40,7 +40,7 @@ def main():
     ext = gsb.native()
     rep = {}
     Path('gpurun_out').mkdir(exist_ok=True)
-    for n in (6, 100, 1000, 2000, 4096, 16384, 20000, 40000, 65536, 100000, 1000000, 3000000):
+    for n in (300, 600, 1000, 65535, 65536, 65537, 65535 + 100, 65535 + 600, 65535 + 3000, 131070 + 1, 3000000):
         g = synth.make_gaussians(n, "1080p", sh_degree=0, seed=n, device=dev)
         cam = synth.make_camera("1080p", device=dev)
         for name, T in poses(dev).items():
@@ -52,6 +52,9 @@ def main():
             if False:
                 np.savez(f"gpurun_out/transform_sample_N{n}_{name}.npz", xyz=g.xyz[:20000].cpu().numpy(), T=T.cpu().numpy(),
                          xyz_cam=xyz_cam[:20000].cpu().numpy())
+            bad = torch.nonzero(a[1] != b[1]).flatten()
+            if 0 < bad.numel() < 50:
+                print("   mismatching rows:", bad.tolist()[:20], flush=True)
             same_z = float((a[1] == b[1]).float().mean())
             ra, rb = a[0].view(torch.int32), b[0].view(torch.int32)
             fin = torch.isfinite(b[0]).all(dim=1)
