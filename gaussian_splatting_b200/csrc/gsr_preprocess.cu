@@ -101,7 +101,7 @@ __device__ __forceinline__ void coop_copy(float* __restrict__ dst, const float* 
 
 template <int N_SH, bool HAS_SH>
 __global__ void __launch_bounds__(PRE_THREADS)
-    k_preprocess_fwd(int N, const float* __restrict__ xyz, const float* __restrict__ xyz_cam,
+    k_preprocess_fwd(int N, const float* __restrict__ xyz, const float* __restrict__ xyz_cam, int cam_first,
                      const float* __restrict__ quat,
                      const float* __restrict__ scale, const float* __restrict__ opa_logit,
                      const float* __restrict__ rgb_dc, const float* __restrict__ sh_rest,
@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(PRE_THREADS)
     if (i < N) {
         const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
         float px, py, pz, u, v;
-        if (xyz_cam != nullptr) {
-            px = xyz_cam[i * 3 + 0]; py = xyz_cam[i * 3 + 1]; pz = xyz_cam[i * 3 + 2];
+        if (xyz_cam != nullptr && i >= cam_first) {
+            const float* pc = xyz_cam + (size_t)(i - cam_first) * 3;
+            px = pc[0]; py = pc[1]; pz = pc[2];
         } else {
             transform_point<float>(vc.T, x, y, z, px, py, pz);
         }
@@ -340,7 +341,7 @@ size_t gsr_preprocess_temp_bytes(int N) {
 }
 
 int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* xyz_camera_frame,
-                           const float* quaternion,
+                           int cam_first, const float* quaternion,
                            const float* scale, const float* opacity_logit, const float* rgb_dc,
                            const float* sh_rest, const float* camera_T_world, const float* K,
                            const float* camera_centre, int H, int W, float near_thresh, float far_thresh,
@@ -356,7 +357,7 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
     const dim3 grid((N + PRE_THREADS - 1) / PRE_THREADS), block(PRE_THREADS);
     const int use_tma = (aligned16(records) && (sh_rest == nullptr || aligned16(sh_rest))) ? 1 : 0;
 #define GSR_PRE_ARGS                                                                              \
-    N, xyz, xyz_camera_frame, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K,          \
+    N, xyz, xyz_camera_frame, cam_first, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K, \
         camera_centre, (float)W, (float)H,                                                                 \
         near_thresh, far_thresh, cull_mask_padding, mh_dist, ntx, nty, records, depth_key, visible, packed, use_tma
     switch (n_sh_rest) {

@@ -426,11 +426,13 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
     TORCH_CHECK(rgb_dc.size(0) == N && rgb_dc.size(1) == 3, "rgb must have shape Nx3");
     TORCH_CHECK(camera_T_world.numel() == 16 && K.numel() == 9, "camera_T_world must be 4x4 and K 3x3");
     const float* cam_ptr = nullptr;
-    if (xyz_camera_frame.has_value()) {
+    int cam_first = 0;
+    if (xyz_camera_frame.has_value()) {  // positions of the LAST xyz_camera_frame.size(0) gaussians
         const torch::Tensor& pc = *xyz_camera_frame;
         CHECK_VALID_INPUT(pc); CHECK_FLOAT_TENSOR(pc);
-        TORCH_CHECK(pc.dim() == 2 && pc.size(0) == N && pc.size(1) == 3, "xyz_camera_frame must have shape Nx3");
+        TORCH_CHECK(pc.dim() == 2 && pc.size(0) <= N && pc.size(1) == 3, "xyz_camera_frame must have shape Rx3, R <= N");
         cam_ptr = pc.data_ptr<float>();
+        cam_first = N - (int)pc.size(0);
     }
     const float* centre_ptr = nullptr;
     if (camera_centre.has_value()) {
@@ -456,7 +458,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
     torch::Tensor scan = torch::empty({N}, opt.dtype(torch::kInt64));
     const size_t tb = gsr_preprocess_temp_bytes(N);
     torch::Tensor temp = torch::empty({(int64_t)tb}, opt.dtype(torch::kUInt8));
-    check_rc(gsr_preprocess_forward(N, n_rest, F32PTR(xyz), cam_ptr, F32PTR(quaternion), F32PTR(scale),
+    check_rc(gsr_preprocess_forward(N, n_rest, F32PTR(xyz), cam_ptr, cam_first, F32PTR(quaternion), F32PTR(scale),
                                     F32PTR(opacity_logit), F32PTR(rgb_dc), sh_ptr, F32PTR(camera_T_world),
                                     F32PTR(K), centre_ptr, (int)H, (int)W, (float)near_thresh, (float)far_thresh,
                                     (float)cull_mask_padding, (float)mh_dist, F32PTR(records),

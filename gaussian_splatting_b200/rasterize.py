@@ -44,6 +44,8 @@ import os
 # torch.matmul exactly as the reference does (splat_py/utils.py:60-72).
 IN_KERNEL_TRANSFORM = os.environ.get("GSR_TORCH_TRANSFORM", "0") != "1"
 IN_KERNEL_TRANSFORM_MIN_N = 16384
+CUBLAS_BATCH_CHUNK = 65535   # gridDim limit cuBLAS batches against
+SMALL_BATCH = 1024           # chunks below ~300 use another kernel (measured: 100 differs, 300 matches)
 
 
 class _ViewState:
@@ -84,8 +86,14 @@ class _ProjectGaussians(torch.autograd.Function):
         # camera-frame positions: by default formed exactly like the reference does (torch.matmul,
         # splat_py/utils.py:60-72), because their bits decide tile membership and the 1/255 skip and the
         # rounding order inside cuBLAS is not ours to pin; IN_KERNEL_TRANSFORM folds it into the kernel.
-        in_kernel = IN_KERNEL_TRANSFORM and xyz.shape[0] >= IN_KERNEL_TRANSFORM_MIN_N
-        xyz_cam = None if in_kernel else transform_points_torch(xyz, camera_T_world)
+        N = xyz.shape[0]
+        if IN_KERNEL_TRANSFORM and N >= IN_KERNEL_TRANSFORM_MIN_N:
+            # cuBLAS runs the batched product in chunks of 65535 matrices; a short last chunk goes through
+            # its small-batch kernel (different rounding order), so that tail is formed by torch itself
+            tail = N % CUBLAS_BATCH_CHUNK
+            xyz_cam = transform_points_torch(xyz[N - tail:], camera_T_world) if 0 < tail < SMALL_BATCH else None
+        else:
+            xyz_cam = transform_points_torch(xyz, camera_T_world)
         # camera centre for the SH view direction: same LU-based inverse as the reference's torch.inverse
         # (splat_py/rasterize.py:91-93), through inv_ex so that no host sync is involved
         centre = None

@@ -179,9 +179,10 @@ size_t gsr_preprocess_temp_bytes(int N);
 /* inputs: xyz [N,3], quaternion [N,4], scale [N,3], opacity_logit [N], rgb_dc [N,3],
  *         sh_rest [N,3,n_sh_rest] (n_sh_rest in {0,3,8,15}; may be NULL when 0),
  *         camera_T_world [4,4] and K [3,3] ON DEVICE;
- *         xyz_camera_frame [N,3] or NULL: camera-frame positions computed by the caller (the reference
- *         forms them with torch.matmul, whose rounding order belongs to cuBLAS); when NULL the kernel
- *         applies camera_T_world itself with the same rounding order;
+ *         xyz_camera_frame [N - cam_first, 3] or NULL: camera-frame positions of gaussians cam_first..N-1
+ *         computed by the caller (the reference forms them with torch.matmul, whose rounding order
+ *         belongs to cuBLAS); for every other gaussian the kernel applies camera_T_world itself,
+ *         reproducing the rounding order of cuBLAS' large-batch kernel (csrc/gsr_math.cuh);
  *         camera_centre [3] or NULL: inverse(camera_T_world)[:3,3] computed by the caller (the reference
  *         uses torch.inverse); when NULL the kernel inverts the pose itself (fp64 Gauss-Jordan).
  * outputs (all indexed by ORIGINAL gaussian index):
@@ -191,7 +192,7 @@ size_t gsr_preprocess_temp_bytes(int N);
  *   scan     uint64 [N]     INCLUSIVE scan of (visible << 32 | tiles_touched);
  *                           scan[N-1] >> 32 == M, scan[N-1] & 0xffffffff == P */
 int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* xyz_camera_frame,
-                           const float* quaternion,
+                           int cam_first, const float* quaternion,
                            const float* scale, const float* opacity_logit, const float* rgb_dc,
                            const float* sh_rest, const float* camera_T_world, const float* K,
                            const float* camera_centre, int H, int W, float near_thresh, float far_thresh,

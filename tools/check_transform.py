@@ -40,12 +40,15 @@ def main():
     ext = gsb.native()
     rep = {}
     Path('gpurun_out').mkdir(exist_ok=True)
-    for n in (300, 600, 1000, 65535, 65536, 65537, 65535 + 100, 65535 + 600, 65535 + 3000, 131070 + 1, 3000000):
+    for n in (6, 300, 1000, 20000, 65535, 65536, 65537, 65535 + 100, 65535 + 290, 65535 + 600, 131070 + 1, 1000000, 3000000):
         g = synth.make_gaussians(n, "1080p", sh_degree=0, seed=n, device=dev)
         cam = synth.make_camera("1080p", device=dev)
         for name, T in poses(dev).items():
             xyz_cam = transform_points_torch(g.xyz, T)
-            a = ext.fused_preprocess_forward(g.xyz, None, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, None, T,
+            tail = n % 65535
+            cam_tail = transform_points_torch(g.xyz[n - tail:], T) if (n >= 16384 and 0 < tail < 1024) else (
+                xyz_cam if n < 16384 else None)
+            a = ext.fused_preprocess_forward(g.xyz, cam_tail, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, None, T,
                                              cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0)
             b = ext.fused_preprocess_forward(g.xyz, xyz_cam, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, None, T,
                                              cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0)
