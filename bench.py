@@ -172,18 +172,35 @@ def run_b200(args, rank, world, local):
     h2d_bytes = poses_host[0].numel() * 4 + K_host.numel() * 4 + G_host.numel() * 4
     d2h_bytes = image_host.numel() * 4
 
-    def step_e2e(i):
-        from gaussian_splatting_b200.structs import Camera
+    # e2e: host buffers in, host buffer out, every step.  Copies run on a side stream so that the 25 MB
+    # upstream-gradient upload overlaps the forward pass and the 25 MB image download overlaps the backward
+    # pass; the step ends with a full synchronize (its result is on the host before the next step starts).
+    from gaussian_splatting_b200.structs import Camera
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    T_buf, K_buf = torch.empty(4, 4, device=dev), torch.empty(3, 3, device=dev)
+    G_buf = torch.empty_like(G)
+    cam_e2e = Camera(cam.width, cam.height, K_buf)
+
+    def step_e2e(i):
+        main = torch.cuda.current_stream()
         zero_grads(g)
-        T_dev = poses_host[view_of(i)].to(dev, non_blocking=True)
-        K_dev = K_host.to(dev, non_blocking=True)
-        G_dev = G_host.to(dev, non_blocking=True)
-        image, _, _ = rasterize(g, T_dev, Camera(cam.width, cam.height, K_dev), cfg["near_thresh"], cfg["far_thresh"],
+        with torch.cuda.stream(copy_stream):
+            T_buf.copy_(poses_host[view_of(i)], non_blocking=True)
+            K_buf.copy_(K_host, non_blocking=True)
+            ev_small = copy_stream.record_event()
+            G_buf.copy_(G_host, non_blocking=True)
+            ev_grad = copy_stream.record_event()
+        main.wait_event(ev_small)
+        image, _, _ = rasterize(g, T_buf, cam_e2e, cfg["near_thresh"], cfg["far_thresh"],
                                 cfg["cull_mask_padding"], cfg["mh_dist"], True, bg)
-        image_host.copy_(image.detach(), non_blocking=True)
-        image.backward(G_dev)
-        torch.cuda.synchronize()  # the step's result is on the host before the next step starts
+        ev_img = main.record_event()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_img)
+            image_host.copy_(image.detach(), non_blocking=True)
+        main.wait_event(ev_grad)
+        image.backward(G_buf)
+        torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:

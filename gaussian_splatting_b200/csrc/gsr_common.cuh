@@ -12,7 +12,7 @@ constexpr int TILE_PIXELS = 256;
 constexpr int REC = GSR_REC_FLOATS; // floats per splat record
 
 // record slots: three 16-byte lanes
-//   q0 = (u, v, r2skip, opacity)   everything the per-warp footprint test needs
+//   q0 = (u, v, tau', opacity)     tau' = inflated Mahalanobis threshold beyond which alpha < 1/255
 //   q1 = (a, 2b, c, det)           a = conic0 + 0.25, 2b = conic1, c = conic2 + 0.25, det = a*c - b*b
 //   q2 = (rcp, colR, colG, colB)   rcp = Newton-refined 1/det (0 when det is outside the safe range),
 //                                  col = SH_0 * rgb

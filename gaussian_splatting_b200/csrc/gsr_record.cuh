@@ -5,21 +5,32 @@
 
 namespace gsr {
 
-// Squared pixel distance beyond which this splat provably contributes nothing to a pixel, i.e.
-// alpha = opacity * exp(-mh/2) stays below the reference's 1/255 skip threshold:
-//   mh = d^T Sigma^-1 d >= |d|^2 / lambda_max   and   alpha < t  <=  mh > 2 ln(opacity / t).
-// The bound is inflated (6% + a condition-number term + 1 px^2) so that neither the fp32 rounding of
-// mh in the kernels nor the few-ulp error of ex2.approx can make a culled pixel pass the reference's
-// test; culling is therefore invisible in the results (checked bitwise against the reference).
+// Culling bound stored in the record: tau' such that a pixel at offset d from the mean with
+// d^T Sigma^-1 d > tau' provably has alpha = opacity * exp(-mh/2) below the reference's 1/255 skip
+// threshold (alpha < t  <=  mh > 2 ln(opacity / t)).  tau' is the exact bound inflated by 6% plus a
+// condition-number term, and the footprint tests add 1 px^2 of slack, so that neither the fp32 rounding of
+// mh in the kernels nor the few-ulp error of ex2.approx can make a culled pixel pass the reference's test;
+// culling is therefore invisible in the results (checked bitwise against the reference).
 // Returns -1 when the splat can never reach the threshold, +inf when nothing can be proven.
-__device__ __forceinline__ float cull_radius_sq(float a, float bh, float c, float det, float opa) {
+__device__ __forceinline__ float cull_tau(float a, float bh, float c, float det, float opa) {
     if (!(opa > 0.0039137f)) return -1.0f;  // 0.998 / 255: opacity * g <= opacity can never reach 1/255
     if (!(det > 0.0f) || !(a > 0.0f) || !(c > 0.0f)) return __int_as_float(0x7f800000);
     const float hd = 0.5f * (a - c);
     const float lam = 0.5f * (a + c) + sqrtf(hd * hd + bh * bh);  // lambda_max of [[a,b],[b,c]]
     const float tau = fmaxf(2.0f * logf(opa * 255.6f), 0.0f);
-    const float r2 = (1.06f + 4e-6f * (lam * lam / det)) * tau * lam + 1.0f;
-    return (r2 == r2) ? r2 : __int_as_float(0x7f800000);
+    const float t = (1.06f + 4e-6f * (lam * lam / det)) * tau;
+    return (t == t) ? t : __int_as_float(0x7f800000);
+}
+
+// Can the ellipse {d^T Sigma^-1 d <= tau'} (plus 1 px^2 slack) reach a pixel rectangle whose per-axis
+// distances from the splat centre are (dx, dy)?  Necessary conditions: inside the bounding circle of radius
+// sqrt(tau' lambda_max) and inside the axis-aligned bounding box sqrt(tau' a) x sqrt(tau' c).
+__device__ __forceinline__ bool footprint_hits(float dx, float dy, float tau, float a, float b2, float c) {
+    if (!(tau >= 0.0f)) return false;
+    const float dx2 = dx * dx, dy2 = dy * dy;
+    const float hd = 0.5f * (a - c), bh = 0.5f * b2;
+    const float lam = 0.5f * (a + c) + sqrtf(hd * hd + bh * bh);
+    return (dx2 + dy2 <= fmaf(tau, lam * 1.0001f, 1.0f)) && (dx2 <= fmaf(tau, a, 1.0f)) && (dy2 <= fmaf(tau, c, 1.0f));
 }
 
 __device__ __forceinline__ void make_record(float u, float v, float c0, float c1, float c2, float opa,
@@ -42,7 +53,7 @@ __device__ __forceinline__ void make_record(float u, float v, float c0, float c1
     }
     rec[R_U] = u;
     rec[R_V] = v;
-    rec[R_R2] = cull_radius_sq(a, bh, c, det, opa);
+    rec[R_R2] = cull_tau(a, bh, c, det, opa);
     rec[R_OPA] = opa;
     rec[R_A] = a;
     rec[R_B2] = __fadd_rn(bh, bh);
