@@ -213,7 +213,7 @@ def run_b200(args, rank, world, local):
     roofline, stages, stats = None, {}, {}
     if rank == 0:
         prof = []
-        n_prof = max(3, min(args.steps, 10))
+        n_prof = max(5, min(args.steps, 11))
         last_state = None
         for i in range(n_prof):
             zero_grads(g)
@@ -226,7 +226,7 @@ def run_b200(args, rank, world, local):
         acc = {}
         for name, e0, e1 in prof:
             acc.setdefault(name, []).append(e0.elapsed_time(e1))
-        stages = {k: statistics.mean(v) for k, v in acc.items()}
+        stages = {k: statistics.median(v) for k, v in acc.items()}  # median: robust to allocator hiccups
         H, W = cam.height, cam.width
         st = last_state
         npp = st.n_per_pixel
