@@ -410,6 +410,8 @@ def main():
                 run_reference(args, rank, world, local)
             return
         torch.cuda.set_device(local)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     try:
         if args.impl == "reference":
