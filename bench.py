@@ -315,11 +315,69 @@ def cpu_baseline_leg(args, rows=48):
     t_bwd = time.time() - t0
     scale = H / rows
     est = t_proj * 2.0 + t_bin + (t_fwd + t_bwd) * scale  # per-gaussian backward ~ per-gaussian forward
-    return {"value": 1.0 / est, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
+    try:
+        torch_cpu = torch_cpu_projection_sh_leg()
+    except Exception as e:  # never let the auxiliary baseline take the bench down
+        torch_cpu = {"error": repr(e)}
+    return {"value": 1.0 / est, "torch_cpu_projection_sh": torch_cpu, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"CPU oracle (oracle/gsr_oracle.c, OpenMP x{os.cpu_count()}): per-gaussian stage + tile binning "
                       f"for all {N_GAUSS} gaussians, tile renderer fwd+bwd on a {rows}-row band scaled x{scale:.1f}",
             "seconds": {"project": t_proj, "binning": t_bin, "render_fwd_band": t_fwd, "render_bwd_band": t_bwd,
                         "wall": time.time() - t_all}}
+
+
+def torch_cpu_projection_sh_leg(n=N_GAUSS, reps=3):
+    """The reference's PyTorch-CPU projection / SH path (north_star): splat_py.utils.transform_points_torch,
+    the cull expressions of splat_py/rasterize.py:33-49 and batched PyTorch restatements of the per-gaussian
+    operators the reference's analytic_diff.ipynb differentiates (pinhole projection, Sigma_world, Sigma_image,
+    SH -> RGB), forward + backward on the bench's N gaussians, all host threads, median of `reps`."""
+    import torch
+
+    from gaussian_splatting_b200 import synth
+    from gaussian_splatting_b200.utils import quaternion_to_rotation_torch, transform_points_torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = synth.make_gaussians(n, RES, sh_degree=SH_DEGREE, seed=0, requires_grad=True)
+    cam = synth.make_camera(RES)
+    T = synth.make_pose(0, N_POSES)
+    fx, fy, cx, cy = cam.K[0, 0], cam.K[1, 1], cam.K[0, 2], cam.K[1, 2]
+    times = []
+    for _ in range(reps):
+        for p in (g.xyz, g.rgb, g.opacity, g.scale, g.quaternion, g.sh):
+            p.grad = None
+        t0 = time.time()
+        p_cam = transform_points_torch(g.xyz, T)
+        x, y, z = p_cam.unbind(1)
+        uv = torch.stack([fx * x / z + cx, fy * y / z + cy], 1)
+        mask = ((z < 0.3) | (z > 500.0) | (uv[:, 0] < -100) | (uv[:, 0] > cam.width + 100) | (uv[:, 1] < -100)
+                | (uv[:, 1] > cam.height + 100))
+        q = g.quaternion / g.quaternion.norm(dim=1, keepdim=True)
+        R = quaternion_to_rotation_torch(q)
+        RS = R * torch.exp(g.scale).unsqueeze(1)
+        sigma = RS @ RS.transpose(1, 2)
+        zero = torch.zeros_like(z)
+        J = torch.stack([fx / z, zero, -fx * x / (z * z), zero, fy / z, -fy * y / (z * z)], 1).reshape(-1, 2, 3)
+        JW = J @ T[:3, :3]
+        s2 = JW @ sigma @ JW.transpose(1, 2)
+        d = g.xyz - torch.inverse(T)[:3, 3]
+        d = d / d.norm(dim=1, keepdim=True)
+        dx, dy, dz = d.unbind(1)
+        Y = torch.stack([torch.full_like(dx, 0.2820948), -0.4886025 * dy, 0.4886025 * dz, -0.4886025 * dx,
+                         1.0925484 * dx * dy, -1.0925484 * dy * dz, 0.3153916 * (3 * dz * dz - 1),
+                         -1.0925484 * dx * dz, 0.5462742 * (dx * dx - dy * dy),
+                         -0.5900436 * dy * (3 * dx * dx - dy * dy), 2.8906114 * dx * dy * dz,
+                         -0.4570458 * dy * (5 * dz * dz - 1), 0.2638755 * dz * (5 * dz * dz - 3),
+                         -0.4570458 * dx * (5 * dz * dz - 1), 1.4453057 * dz * (dx * dx - dy * dy),
+                         -0.5900436 * dx * (dx * dx - 3 * dy * dy)], 1)
+        rgb = (torch.cat([g.rgb.unsqueeze(2), g.sh], 2) * Y.unsqueeze(1)).sum(2) * 3.5449077
+        keep = (~mask).float()
+        loss = (uv.sum(1) * keep).sum() + (s2.sum((1, 2)) * keep).sum() + (rgb.sum(1) * keep).sum() \
+            + torch.sigmoid(g.opacity).sum()
+        loss.backward()
+        times.append(time.time() - t0)
+    times.sort()
+    return {"seconds_fwd_bwd": times[len(times) // 2], "threads": torch.get_num_threads(), "cores": os.cpu_count(),
+            "gaussians": n}
 
 
 def run_reference(args, rank, world, local):

@@ -21,7 +21,7 @@ constexpr int BIN_THREADS = 256;
 // When keys != nullptr also emits the pairs at keys[base...].
 __device__ __forceinline__ int walk_tiles(const Obb& o, float u, float v, int ntx, int nty,
                                           uint32_t zkey, uint32_t id, uint64_t* __restrict__ keys,
-                                          uint32_t* __restrict__ ids, int64_t base) {
+                                          uint32_t* __restrict__ ids, int64_t base, int depth_bits = 32) {
     int x0, x1, y0, y1;
     tile_window(u, v, o.radius_tiles, ntx, nty, x0, x1, y0, y1);
     int n = 0;
@@ -34,7 +34,7 @@ __device__ __forceinline__ int walk_tiles(const Obb& o, float u, float v, int nt
             if (obb_hits_tile(o, left, right, top, bottom)) {
                 if (keys) {
                     const uint32_t tile = (uint32_t)(ty * ntx + tx);
-                    keys[base + n] = ((uint64_t)tile << 32) | zkey;
+                    keys[base + n] = ((uint64_t)tile << depth_bits) | zkey;
                     ids[base + n] = id;
                 }
                 ++n;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(BIN_THREADS)
 __global__ void __launch_bounds__(BIN_THREADS)
     k_emit_pairs_fused(int N, const float* __restrict__ records,
                        const uint32_t* __restrict__ zkey, const uint8_t* __restrict__ visible,
-                       const uint64_t* __restrict__ scan, int ntx, int nty, float mh,
+                       const uint64_t* __restrict__ scan, int ntx, int nty, float mh, int depth_bits,
                        uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
                        int32_t* __restrict__ vis_idx, float* __restrict__ uv_compact) {
     const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
@@ -93,19 +93,20 @@ __global__ void __launch_bounds__(BIN_THREADS)
     Obb o;
     const float* r = records + (size_t)i * REC;
     compute_obb(u, v, r[R_A], __fmul_rn(r[R_B2], 0.5f), r[R_C], mh, o);
-    walk_tiles(o, u, v, ntx, nty, zkey[i], (uint32_t)i, keys, ids, (int64_t)(prev & 0xffffffffu));
+    walk_tiles(o, u, v, ntx, nty, zkey[i], (uint32_t)i, keys, ids, (int64_t)(prev & 0xffffffffu), depth_bits);
 }
 
 // tile_ranges[t] = first sorted position whose tile id >= t  (ranges[n_tiles] = P).
 // One block stages BIN_THREADS+1 tile ids through shared memory; each position closes the
 // ranges of every tile id in (tile[p-1], tile[p]].
 __global__ void __launch_bounds__(BIN_THREADS)
-    k_tile_ranges(int P, int n_tiles, const uint64_t* __restrict__ keys, int32_t* __restrict__ ranges) {
+    k_tile_ranges(int P, int n_tiles, int depth_bits, const uint64_t* __restrict__ keys,
+                  int32_t* __restrict__ ranges) {
     __shared__ int32_t s_tile[BIN_THREADS + 1];
     const int p0 = blockIdx.x * BIN_THREADS;
     const int p = p0 + threadIdx.x;
-    if (p < P) s_tile[threadIdx.x + 1] = (int32_t)(keys[p] >> 32);
-    if (threadIdx.x == 0) s_tile[0] = (p0 > 0) ? (int32_t)(keys[p0 - 1] >> 32) : -1;
+    if (p < P) s_tile[threadIdx.x + 1] = (int32_t)(keys[p] >> depth_bits);
+    if (threadIdx.x == 0) s_tile[0] = (p0 > 0) ? (int32_t)(keys[p0 - 1] >> depth_bits) : -1;
     __syncthreads();
     if (p >= P) return;
     const int cur = s_tile[threadIdx.x + 1];
@@ -152,10 +153,10 @@ __global__ void __launch_bounds__(BIN_THREADS)
     o[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
 }
 
-static inline int sort_end_bit(int n_tiles) {
+static inline int sort_end_bit(int n_tiles, int depth_bits) {
     int bits = 0;
     while ((1 << bits) < n_tiles) ++bits;
-    return 32 + (bits > 0 ? bits : 1);
+    return depth_bits + (bits > 0 ? bits : 1);
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -196,22 +197,24 @@ size_t gsr_sort_pairs_temp_bytes(int P) {
     return align256(b);
 }
 
-int gsr_sort_pairs(int P, int n_tiles, const uint64_t* keys_in, const uint32_t* ids_in,
+int gsr_sort_pairs(int P, int n_tiles, int depth_bits, const uint64_t* keys_in, const uint32_t* ids_in,
                    uint64_t* keys_out, uint32_t* ids_out, void* temp, size_t temp_bytes, void* stream) {
     if (P <= 0) return GSR_OK;
+    if (depth_bits < 1 || depth_bits > 32) return GSR_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     size_t b = temp_bytes;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, b, keys_in, keys_out, ids_in, ids_out, P, 0,
-                                                    sort_end_bit(n_tiles), st);
+                                                    sort_end_bit(n_tiles, depth_bits), st);
     return (int)e;
 }
 
-int gsr_tile_ranges(int P, int n_tiles, const uint64_t* keys_sorted, int32_t* ranges, void* stream) {
+int gsr_tile_ranges(int P, int n_tiles, int depth_bits, const uint64_t* keys_sorted, int32_t* ranges,
+                    void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (P <= 0) {
         k_fill_i32<<<BGRID(n_tiles + 1)>>>(n_tiles + 1, ranges, 0);
     } else {
-        k_tile_ranges<<<BGRID(P)>>>(P, n_tiles, keys_sorted, ranges);
+        k_tile_ranges<<<BGRID(P)>>>(P, n_tiles, depth_bits, keys_sorted, ranges);
     }
     return (int)cudaGetLastError();
 }
@@ -227,7 +230,7 @@ int gsr_binning_emit_sort(int N, int P, const float* uvs, const float* xyz_cam, 
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = ntx * nty;
     if (temp_bytes < gsr_binning_sort_temp_bytes(P)) return GSR_ERR_BAD_ARG;
-    if (P <= 0) return gsr_tile_ranges(0, n_tiles, nullptr, ranges, stream);
+    if (P <= 0) return gsr_tile_ranges(0, n_tiles, 32, nullptr, ranges, stream);
     const size_t p = (size_t)P;
     char* base = (char*)temp;
     const size_t sort_bytes = gsr_sort_pairs_temp_bytes(P);
@@ -236,18 +239,18 @@ int gsr_binning_emit_sort(int N, int P, const float* uvs, const float* xyz_cam, 
     uint32_t* ids_a = (uint32_t*)((char*)keys_b + align256(8 * p));
     uint32_t* ids_b = (uint32_t*)((char*)ids_a + align256(4 * p));
     k_emit_pairs_api<<<BGRID(N)>>>(N, uvs, xyz_cam, conic, ntx, nty, mh, offsets, keys_a, ids_a);
-    int rc = gsr_sort_pairs(P, n_tiles, keys_a, ids_a, keys_b, ids_b, temp, sort_bytes, stream);
+    int rc = gsr_sort_pairs(P, n_tiles, 32, keys_a, ids_a, keys_b, ids_b, temp, sort_bytes, stream);
     if (rc) return rc;
     k_ids_to_i32<<<BGRID(P)>>>(P, ids_b, sorted_idx);
-    return gsr_tile_ranges(P, n_tiles, keys_b, ranges, stream);
+    return gsr_tile_ranges(P, n_tiles, 32, keys_b, ranges, stream);
 }
 
 int gsr_emit_pairs(int N, const float* records, const uint32_t* depth_key,
-                   const uint8_t* visible, const uint64_t* scan, int ntx, int nty, float mh,
+                   const uint8_t* visible, const uint64_t* scan, int ntx, int nty, float mh, int depth_bits,
                    uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
-    k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, keys,
+    k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, depth_bits, keys,
                                      ids, vis_idx, uv_compact);
     return (int)cudaGetLastError();
 }

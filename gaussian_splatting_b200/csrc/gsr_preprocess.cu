@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(PRE_THREADS)
                      const float* __restrict__ rgb_dc, const float* __restrict__ sh_rest,
                      const float* __restrict__ Tdev, const float* __restrict__ Kdev,
                      const float* __restrict__ camdev, float width, float height, float near_t, float far_t,
-                     float pad, float mh, int ntx, int nty,
+                     float pad, float mh, int ntx, int nty, uint32_t depth_base,
                      float* __restrict__ records, uint32_t* __restrict__ zkey,
                      uint8_t* __restrict__ visible, uint64_t* __restrict__ packed, int use_tma) {
     constexpr int NR3 = HAS_SH ? 3 * (N_SH - 1) : 1;
@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(PRE_THREADS)
         // splat_py/rasterize.py:38-49 (strict compares, fp32)
         const bool culled = (pz < near_t) | (pz > far_t) | (u < -pad) | (u > width + pad) | (v < -pad) |
                             (v > height + pad);
-        zkey[i] = depth_key(pz);
+        // visible => pz >= near > 0: float bits are monotone, and relative to bits(near) only a few low
+        // bits are significant (shorter radix sort)
+        zkey[i] = depth_base ? (__float_as_uint(pz) - depth_base) : depth_key(pz);
         // NaN coordinates compare false everywhere and would survive; the reference aborts on them
         // (splat_py/tile_culling.py:15-18) — treat as culled instead.
         const bool vis = !culled && (pz == pz) && (u == u) && (v == v);
@@ -345,7 +347,8 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
                            const float* scale, const float* opacity_logit, const float* rgb_dc,
                            const float* sh_rest, const float* camera_T_world, const float* K,
                            const float* camera_centre, int H, int W, float near_thresh, float far_thresh,
-                           float cull_mask_padding, float mh_dist, float* records, uint32_t* depth_key,
+                           float cull_mask_padding, float mh_dist, uint32_t depth_base, float* records,
+                           uint32_t* depth_key,
                            uint8_t* visible, uint64_t* scan, void* temp, size_t temp_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
@@ -359,7 +362,8 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
 #define GSR_PRE_ARGS                                                                              \
     N, xyz, xyz_camera_frame, cam_first, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K, \
         camera_centre, (float)W, (float)H,                                                                 \
-        near_thresh, far_thresh, cull_mask_padding, mh_dist, ntx, nty, records, depth_key, visible, packed, use_tma
+        near_thresh, far_thresh, cull_mask_padding, mh_dist, ntx, nty, depth_base, records, depth_key, visible, \
+        packed, use_tma
     switch (n_sh_rest) {
         case 0: k_preprocess_fwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
         case 3: k_preprocess_fwd<4, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;

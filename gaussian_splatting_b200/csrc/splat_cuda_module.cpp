@@ -412,7 +412,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
     torch::Tensor xyz, c10::optional<torch::Tensor> xyz_camera_frame, torch::Tensor quaternion, torch::Tensor scale,
     torch::Tensor opacity_logit, torch::Tensor rgb_dc, c10::optional<torch::Tensor> sh_rest,
     torch::Tensor camera_T_world, torch::Tensor K, c10::optional<torch::Tensor> camera_centre, int64_t H, int64_t W,
-    double near_thresh, double far_thresh, double cull_mask_padding, double mh_dist) {
+    double near_thresh, double far_thresh, double cull_mask_padding, double mh_dist, int64_t depth_base) {
     CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(quaternion); CHECK_VALID_INPUT(scale); CHECK_VALID_INPUT(opacity_logit);
     CHECK_VALID_INPUT(rgb_dc); CHECK_VALID_INPUT(camera_T_world); CHECK_VALID_INPUT(K);
     CHECK_FLOAT_TENSOR(xyz); CHECK_FLOAT_TENSOR(quaternion); CHECK_FLOAT_TENSOR(scale);
@@ -461,7 +461,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
     check_rc(gsr_preprocess_forward(N, n_rest, F32PTR(xyz), cam_ptr, cam_first, F32PTR(quaternion), F32PTR(scale),
                                     F32PTR(opacity_logit), F32PTR(rgb_dc), sh_ptr, F32PTR(camera_T_world),
                                     F32PTR(K), centre_ptr, (int)H, (int)W, (float)near_thresh, (float)far_thresh,
-                                    (float)cull_mask_padding, (float)mh_dist, F32PTR(records),
+                                    (float)cull_mask_padding, (float)mh_dist, (uint32_t)depth_base, F32PTR(records),
                                     (uint32_t*)zkey.data_ptr<int>(), visible.data_ptr<uint8_t>(),
                                     (uint64_t*)scan.data_ptr<int64_t>(), temp.data_ptr(), tb, cur_stream()),
              "gsr_preprocess_forward");
@@ -472,7 +472,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
 //                 vis_idx [M] i32, uv [M,2]
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_bin(
     torch::Tensor records, torch::Tensor zkey, torch::Tensor visible, torch::Tensor scan, int64_t M, int64_t P,
-    int64_t H, int64_t W, double mh_dist) {
+    int64_t H, int64_t W, double mh_dist, int64_t depth_bits) {
     const int N = records.size(0);
     const int ntx = (W + 15) / 16, nty = (H + 15) / 16, n_tiles = ntx * nty;
     c10::cuda::CUDAGuard guard(records.device());
@@ -490,15 +490,17 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
     uint64_t* keys_b = keys_a + Pa;
     check_rc(gsr_emit_pairs(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(),
                             visible.data_ptr<uint8_t>(), (const uint64_t*)scan.data_ptr<int64_t>(), ntx, nty,
-                            (float)mh_dist, keys_a, (uint32_t*)ids.data_ptr<int>(), vis_idx.data_ptr<int>(),
+                            (float)mh_dist, (int)depth_bits, keys_a, (uint32_t*)ids.data_ptr<int>(),
+                            vis_idx.data_ptr<int>(),
                             F32PTR(uv), cur_stream()),
              "gsr_emit_pairs");
     const size_t sb = gsr_sort_pairs_temp_bytes((int)P);
     torch::Tensor temp = torch::empty({(int64_t)sb}, opt.dtype(torch::kUInt8));
-    check_rc(gsr_sort_pairs((int)P, n_tiles, keys_a, (const uint32_t*)ids.data_ptr<int>(), keys_b,
+    check_rc(gsr_sort_pairs((int)P, n_tiles, (int)depth_bits, keys_a, (const uint32_t*)ids.data_ptr<int>(), keys_b,
                             (uint32_t*)ids_sorted.data_ptr<int>(), temp.data_ptr(), sb, cur_stream()),
              "gsr_sort_pairs");
-    check_rc(gsr_tile_ranges((int)P, n_tiles, keys_b, ranges.data_ptr<int>(), cur_stream()), "gsr_tile_ranges");
+    check_rc(gsr_tile_ranges((int)P, n_tiles, (int)depth_bits, keys_b, ranges.data_ptr<int>(), cur_stream()),
+             "gsr_tile_ranges");
     check_rc(gsr_gather_records((int)P, (const uint32_t*)ids_sorted.data_ptr<int>(), F32PTR(records),
                                 F32PTR(stream_rec), cur_stream()),
              "gsr_gather_records");

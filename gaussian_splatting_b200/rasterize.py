@@ -48,6 +48,20 @@ CUBLAS_BATCH_CHUNK = 65535   # gridDim limit cuBLAS batches against
 SMALL_BATCH = 1024           # chunks below ~300 use another kernel (measured: 100 differs, 300 matches)
 
 
+def _depth_key_params(near, far):
+    """(base, bits): depth keys are float bits of z minus `base`; `bits` low bits are significant."""
+    import math
+    import struct
+
+    def fbits(v):
+        return struct.unpack("<I", struct.pack("<f", v))[0]
+
+    if near > 0.0 and math.isfinite(far) and far > near:
+        b0, b1 = fbits(near), fbits(far)
+        return b0, max(1, (b1 - b0).bit_length())
+    return 0, 32
+
+
 class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
@@ -82,6 +96,7 @@ class _ProjectGaussians(torch.autograd.Function):
     def forward(ctx, xyz, quaternion, scale, opacity, rgb, sh, camera_T_world, K, state, cfg):
         ext = native()
         H, W, near, far, pad, mh = cfg
+        depth_base, depth_bits = _depth_key_params(near, far)
         opacity_flat = opacity.reshape(-1)
         # camera-frame positions: by default formed exactly like the reference does (torch.matmul,
         # splat_py/utils.py:60-72), because their bits decide tile membership and the 1/255 skip and the
@@ -102,11 +117,12 @@ class _ProjectGaussians(torch.autograd.Function):
         with _stage(state, "preprocess_fwd"):
             records, zkey, visible, scan = ext.fused_preprocess_forward(
                 xyz, xyz_cam, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, centre, H, W, near, far,
-                pad, mh)
+                pad, mh, depth_base)
         total = int(scan[-1].item()) if xyz.shape[0] > 0 else 0  # the one host sync
         M, P = total >> 32, total & 0xFFFFFFFF
         with _stage(state, "bin_sort_gather"):
-            ids_sorted, ranges, stream_rec, vis_idx, uv = ext.fused_bin(records, zkey, visible, scan, M, P, H, W, mh)
+            ids_sorted, ranges, stream_rec, vis_idx, uv = ext.fused_bin(records, zkey, visible, scan, M, P, H, W, mh,
+                                                                        depth_bits)
         state.N, state.M, state.P, state.H, state.W = xyz.shape[0], M, P, H, W
         state.visible, state.vis_idx = visible, vis_idx.long()  # int64: index_copy_ needs it
         state.ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec

@@ -187,7 +187,9 @@ size_t gsr_preprocess_temp_bytes(int N);
  *         uses torch.inverse); when NULL the kernel inverts the pose itself (fp64 Gauss-Jordan).
  * outputs (all indexed by ORIGINAL gaussian index):
  *   records  float [N,12]   packed splat record (undefined for culled rows)
- *   depth_key uint32 [N]    order-preserving key of camera-frame z
+ *   depth_key uint32 [N]    order-preserving key of camera-frame z: float bits of z minus depth_base
+ *                           (pass depth_base = float bits of near_thresh when near_thresh > 0 so that only
+ *                           bitlength(bits(far) - bits(near)) low bits are significant; 0 otherwise)
  *   visible  uint8 [N]      1 = survives the frustum cull (culling_mask = !visible)
  *   scan     uint64 [N]     INCLUSIVE scan of (visible << 32 | tiles_touched);
  *                           scan[N-1] >> 32 == M, scan[N-1] & 0xffffffff == P */
@@ -196,21 +198,24 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
                            const float* scale, const float* opacity_logit, const float* rgb_dc,
                            const float* sh_rest, const float* camera_T_world, const float* K,
                            const float* camera_centre, int H, int W, float near_thresh, float far_thresh,
-                           float cull_mask_padding, float mh_dist, float* records, uint32_t* depth_key,
+                           float cull_mask_padding, float mh_dist, uint32_t depth_base, float* records,
+                           uint32_t* depth_key,
                            uint8_t* visible, uint64_t* scan, void* temp, size_t temp_bytes, void* stream);
 
 /* emits the (tile, depth) keys and original-gaussian ids of all P pairs, the compact list of
  * visible gaussian ids vis_idx int32 [M] and the compacted uv [M,2] the reference returns */
+/* keys are (tile << depth_bits) | depth_key; depth_bits in 1..32 is the number of significant key bits */
 int gsr_emit_pairs(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
-                   const uint64_t* scan, int n_tiles_x, int n_tiles_y, float mh_dist,
+                   const uint64_t* scan, int n_tiles_x, int n_tiles_y, float mh_dist, int depth_bits,
                    uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, void* stream);
 
 size_t gsr_sort_pairs_temp_bytes(int P);
-int gsr_sort_pairs(int P, int n_tiles, const uint64_t* keys_in, const uint32_t* ids_in,
+int gsr_sort_pairs(int P, int n_tiles, int depth_bits, const uint64_t* keys_in, const uint32_t* ids_in,
                    uint64_t* keys_out, uint32_t* ids_out, void* temp, size_t temp_bytes, void* stream);
 
 /* tile_ranges int32 [n_tiles+1] from sorted keys */
-int gsr_tile_ranges(int P, int n_tiles, const uint64_t* keys_sorted, int32_t* tile_ranges, void* stream);
+int gsr_tile_ranges(int P, int n_tiles, int depth_bits, const uint64_t* keys_sorted, int32_t* tile_ranges,
+                    void* stream);
 
 /* records_sorted[p] = records[ids_sorted[p]] (48-byte rows) */
 int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, float* records_sorted,

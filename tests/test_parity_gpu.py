@@ -291,7 +291,7 @@ def test_in_kernel_transform_reproduces_torch_matmul(n):
     cam_tail = transform_points_torch(g.xyz[n - tail:], T) if 0 < tail < R.SMALL_BATCH else None
     ext = gsb.native()
     rec, zkey, vis, scan = ext.fused_preprocess_forward(g.xyz, cam_tail, g.quaternion, g.scale, g.opacity.reshape(-1),
-                                                        g.rgb, None, T, cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0)
+                                                        g.rgb, None, T, cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0, 0)
     zref = ref[:, 2].contiguous().view(torch.int32)
     zref = torch.where(zref < 0, ~zref, zref | -2**31)
     assert_bits_equal(zkey, zref, "depth key (camera z)")

@@ -49,9 +49,9 @@ def main():
             cam_tail = transform_points_torch(g.xyz[n - tail:], T) if (n >= 16384 and 0 < tail < 1024) else (
                 xyz_cam if n < 16384 else None)
             a = ext.fused_preprocess_forward(g.xyz, cam_tail, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, None, T,
-                                             cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0)
+                                             cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0, 0)
             b = ext.fused_preprocess_forward(g.xyz, xyz_cam, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, None, T,
-                                             cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0)
+                                             cam.K, None, 1080, 1920, -1e30, 1e30, 1e30, 3.0, 0)
             if False:
                 np.savez(f"gpurun_out/transform_sample_N{n}_{name}.npz", xyz=g.xyz[:20000].cpu().numpy(), T=T.cpu().numpy(),
                          xyz_cam=xyz_cam[:20000].cpu().numpy())

@@ -191,7 +191,7 @@ def main():
         sh = g.sh
         rec, zkey, vis, scan = ext.fused_preprocess_forward(
             g.xyz, None, g.quaternion, g.scale, g.opacity.reshape(-1), g.rgb, sh, T, cam.K, None, H, W,
-            cfg["near_thresh"], cfg["far_thresh"], cfg["cull_mask_padding"], cfg["mh_dist"])
+            cfg["near_thresh"], cfg["far_thresh"], cfg["cull_mask_padding"], cfg["mh_dist"], 0)
         xyz_cam = state["xyz_cam"]
         uv = state["uv"]
         mask = ((xyz_cam[:, 2] < cfg["near_thresh"]) | (xyz_cam[:, 2] > cfg["far_thresh"])
