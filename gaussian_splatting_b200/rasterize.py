@@ -195,41 +195,46 @@ def rasterize(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_m
     return image, culling_mask, uv
 
 
-def rasterize_unfused(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist,
-                      use_sh_precompute, background_rgb):
-    """Operator-by-operator evaluation, one native op per reference op (any dtype, any SH mode)."""
+def project_and_bin(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist):
+    """The per-gaussian part of the reference chain, one native op per reference op (any dtype):
+    transform -> pinhole -> frustum cull -> Sigma_world / J / conic -> tile binning.  Returns a namespace with
+    culling_mask [N] and, for the survivors, uv, xyz_cam, xyz, opacity (post-sigmoid), rgb, sh, conic,
+    sorted_idx, tile_ranges."""
+    from types import SimpleNamespace
+
     xyz_cam = transform_points_torch(gaussians.xyz, camera_T_world)
     uv = CameraPointProjection.apply(xyz_cam, camera.K)
-    z = xyz_cam[:, 2]
+    z, pad = xyz_cam[:, 2], cull_mask_padding
     culling_mask = (
         (z < near_thresh) | (z > far_thresh)
-        | (uv[:, 0] < -1 * cull_mask_padding) | (uv[:, 0] > camera.width + cull_mask_padding)
-        | (uv[:, 1] < -1 * cull_mask_padding) | (uv[:, 1] > camera.height + cull_mask_padding)
+        | (uv[:, 0] < -1 * pad) | (uv[:, 0] > camera.width + pad)
+        | (uv[:, 1] < -1 * pad) | (uv[:, 1] > camera.height + pad)
     )
     keep = ~culling_mask
-    uv, xyz_cam = uv[keep, :], xyz_cam[keep, :]
-    xyz_w = gaussians.xyz[keep, :]
-    opacity = torch.sigmoid(gaussians.opacity[keep])
-    rgb = gaussians.rgb[keep, :]
-    sh = None if gaussians.sh is None else gaussians.sh[keep, :]
-
+    s = SimpleNamespace(culling_mask=culling_mask, uv=uv[keep, :], xyz_cam=xyz_cam[keep, :], xyz=gaussians.xyz[keep, :],
+                        opacity=torch.sigmoid(gaussians.opacity[keep]), rgb=gaussians.rgb[keep, :],
+                        sh=None if gaussians.sh is None else gaussians.sh[keep, :])
     sigma_world = ComputeSigmaWorld.apply(gaussians.quaternion[keep, :], gaussians.scale[keep, :])
-    J = ComputeProjectionJacobian.apply(xyz_cam, camera.K)
-    conic = ComputeConic.apply(sigma_world, J, camera_T_world)
-
+    J = ComputeProjectionJacobian.apply(s.xyz_cam, camera.K)
+    s.conic = ComputeConic.apply(sigma_world, J, camera_T_world)
     tiles = Tiles(camera.height, camera.width, uv.device)
-    sorted_idx, tile_ranges = get_splats(uv.detach(), tiles, conic.detach(), xyz_cam.detach(), mh_dist)
+    s.sorted_idx, s.tile_ranges = get_splats(s.uv.detach(), tiles, s.conic.detach(), s.xyz_cam.detach(), mh_dist)
+    return s
 
-    rays = torch.zeros(1, 1, 1, dtype=gaussians.xyz.dtype, device=gaussians.xyz.device)
-    if sh is not None:
-        coeffs = torch.cat((rgb.unsqueeze(dim=2), sh), dim=2)
-        if use_sh_precompute:
-            render_rgb = PrecomputeRGBFromSH.apply(coeffs, xyz_w, torch.inverse(camera_T_world).contiguous())
-        else:
-            render_rgb = coeffs
-            rays = compute_rays_in_world_frame(camera, camera_T_world)
+
+def rasterize_unfused(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist,
+                      use_sh_precompute, background_rgb):
+    """Operator-by-operator evaluation (any dtype, either SH mode); same return triple as rasterize()."""
+    s = project_and_bin(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist)
+    rays = torch.zeros(1, 1, 1, dtype=gaussians.xyz.dtype, device=gaussians.xyz.device)  # unused unless per-pixel SH
+    if s.sh is None:
+        render_rgb = s.rgb
     else:
-        render_rgb = rgb
-    image = RenderImage.apply(render_rgb, opacity, uv, conic, rays, tile_ranges, sorted_idx,
+        coeffs = torch.cat((s.rgb.unsqueeze(dim=2), s.sh), dim=2)
+        if use_sh_precompute:
+            render_rgb = PrecomputeRGBFromSH.apply(coeffs, s.xyz, torch.inverse(camera_T_world).contiguous())
+        else:
+            render_rgb, rays = coeffs, compute_rays_in_world_frame(camera, camera_T_world)
+    image = RenderImage.apply(render_rgb, s.opacity, s.uv, s.conic, rays, s.tile_ranges, s.sorted_idx,
                               (camera.height, camera.width), background_rgb)
-    return image, culling_mask, uv
+    return image, s.culling_mask, s.uv

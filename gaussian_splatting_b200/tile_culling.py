@@ -3,19 +3,15 @@ from __future__ import annotations
 
 from . import native
 
+MAX_TILES_PER_GAUSSIAN = 1024  # accepted and ignored by the native op, exactly as in the reference
+
 
 def get_splats(uvs, tiles, conic, xyz_camera_frame, mh_dist):
-    """-> (sorted_gaussian_idx_by_splat_idx int32 [P], splat_start_end_idx_by_tile_idx int32 [T+1]).
+    """(gaussian, tile) pairs of the mh_dist-sigma footprints, ordered by (tile, camera depth, gaussian index).
 
-    The reference aborts the process on non-finite xyz (a host sync); here non-finite depths
-    simply sort last inside their tile.
+    Returns ``(sorted_gaussian_idx_by_splat_idx int32 [P], splat_start_end_idx_by_tile_idx int32 [tiles + 1])``:
+    the splats of tile t are ``sorted[ranges[t]:ranges[t + 1]]``.  One host sync (to size the outputs).
+    Unlike the reference there is no process exit on non-finite positions: such points sort last in their tile.
     """
-    return native().get_sorted_gaussian_list(
-        1024,  # max_tiles_per_gaussian: accepted and ignored, as in the reference
-        uvs,
-        xyz_camera_frame,
-        conic,
-        tiles.x_tiles_count,
-        tiles.y_tiles_count,
-        mh_dist,
-    )
+    nx, ny = tiles.x_tiles_count, tiles.y_tiles_count
+    return native().get_sorted_gaussian_list(MAX_TILES_PER_GAUSSIAN, uvs, xyz_camera_frame, conic, nx, ny, mh_dist)

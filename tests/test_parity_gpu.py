@@ -135,6 +135,20 @@ def test_golden_fixture6_rasterize(mode):
         assert_bits_equal(r["image"], ref_img, "image")
 
 
+def test_render_depth_known_answers():
+    """test/test_depth.py:33,36 — range to the first surface above alpha 0.2 on the reference fixture."""
+    from gaussian_splatting_b200.depth import render_depth
+
+    fx = scenes.reference_fixture()
+    fx = dict(fx, opacity=scenes.inverse_sigmoid(fx["opacity"]))
+    g = gaussians_from(fx, requires_grad=False)
+    depth = render_depth(g, 0.2, to_t(fx["T"]), Camera(640, 480, to_t(fx["K"])), 0.3, 10, 3.0)
+    assert depth.shape == (480, 640, 1)
+    assert abs(depth[340, 348].item() - 17.29551887512207) < 5e-5
+    assert abs(depth[200, 348].item() - 13.205718040466309) < 5e-5
+    assert depth[0, 0].item() == -1.0
+
+
 @pytest.mark.parametrize("name,nG,res,sig,shd", [
     ("synth_tiny", 2000, "tiny", (2.0, 0.5, 0.5, 8.0), 3),
     ("synth_small", 12000, "small", (2.5, 0.5, 0.5, 10.0), 3),
