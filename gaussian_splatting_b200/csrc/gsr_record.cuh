@@ -22,15 +22,28 @@ __device__ __forceinline__ float cull_tau(float a, float bh, float c, float det,
     return (t == t) ? t : __int_as_float(0x7f800000);
 }
 
-// Can the ellipse {d^T Sigma^-1 d <= tau'} (plus 1 px^2 slack) reach a pixel rectangle whose per-axis
-// distances from the splat centre are (dx, dy)?  Necessary conditions: inside the bounding circle of radius
-// sqrt(tau' lambda_max) and inside the axis-aligned bounding box sqrt(tau' a) x sqrt(tau' c).
-__device__ __forceinline__ bool footprint_hits(float dx, float dy, float tau, float a, float b2, float c) {
-    if (!(tau >= 0.0f)) return false;
-    const float dx2 = dx * dx, dy2 = dy * dy;
+// Necessary conditions for the ellipse {d^T Sigma^-1 d <= tau'} (plus 1 px^2 slack) to reach a pixel
+// rectangle whose per-axis distances from the splat centre are (dx, dy): inside the bounding circle of
+// radius sqrt(tau' lambda_max) and inside the axis-aligned bounding box sqrt(tau' a) x sqrt(tau' c).
+struct FootprintBounds {
+    float r2, hx2, hy2;  // squared limits; all negative when the splat can never contribute
+};
+__device__ __forceinline__ FootprintBounds footprint_bounds(float tau, float a, float b2, float c) {
+    FootprintBounds f;
+    if (!(tau >= 0.0f)) {
+        f.r2 = f.hx2 = f.hy2 = -1.0f;
+        return f;
+    }
     const float hd = 0.5f * (a - c), bh = 0.5f * b2;
     const float lam = 0.5f * (a + c) + sqrtf(hd * hd + bh * bh);
-    return (dx2 + dy2 <= fmaf(tau, lam * 1.0001f, 1.0f)) && (dx2 <= fmaf(tau, a, 1.0f)) && (dy2 <= fmaf(tau, c, 1.0f));
+    f.r2 = fmaf(tau, lam * 1.0001f, 1.0f);
+    f.hx2 = fmaf(tau, a, 1.0f);
+    f.hy2 = fmaf(tau, c, 1.0f);
+    return f;
+}
+__device__ __forceinline__ bool footprint_hits(const FootprintBounds& f, float dx, float dy) {
+    const float dx2 = dx * dx, dy2 = dy * dy;
+    return (dx2 + dy2 <= f.r2) && (dx2 <= f.hx2) && (dy2 <= f.hy2);
 }
 
 __device__ __forceinline__ void make_record(float u, float v, float c0, float c1, float c2, float opa,
