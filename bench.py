@@ -260,6 +260,16 @@ def run_b200(args, rank, world, local):
                 other.append(dict(kernel=kname, bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
                                   algorithmic_bytes=nbytes, duration_ms=stages[stage],
                                   note="stage time includes the kernel's cub scan / output allocation"))
+        # instruction-issue roofline of the same kernel: warp instructions per launch from the committed ncu
+        # capture / live duration, against 148 SMs x 4 schedulers x max SM clock
+        issue = None
+        if tf.exists():
+            ninst = json.loads(tf.read_text()).get("k_render_bwd", {}).get("warp_instructions_per_launch")
+            if ninst:
+                peak_issue = 148 * 4 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+                issue = dict(achieved=ninst / (dur_ms * 1e-3) / 1e9, peak=peak_issue / 1e9, unit="G warp-inst/s",
+                             frac=ninst / (dur_ms * 1e-3) / peak_issue,
+                             source="smsp__inst_executed.sum of the committed ncu capture / live CUDA-event duration")
         roofline = dict(kernel="k_render_bwd", bound="hbm", achieved=achieved, peak=peak, unit="GB/s",
                         frac=achieved / peak, traffic=traffic,
                         peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
@@ -267,7 +277,7 @@ def run_b200(args, rank, world, local):
                         note="76 B per (gaussian,tile) pair the kernel has to visit + 20 B per pixel; the kernel is "
                              "instruction-issue bound (ncu: issue slots 80% busy, DRAM 4% of peak; "
                              "profiles/r01_ncu_full_render_kernels_v3.json), so frac is small by construction",
-                        other_kernels=other)
+                        issue_roofline=issue, other_kernels=other)
 
     cpu = cpu_baseline_leg(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
