@@ -14,7 +14,7 @@ constexpr int REC = GSR_REC_FLOATS; // floats per splat record
 // record slots: three 16-byte lanes
 //   q0 = (u, v, tau', opacity)     tau' = inflated Mahalanobis threshold beyond which alpha < 1/255
 //   q1 = (a, 2b, c, det)           a = conic0 + 0.25, 2b = conic1, c = conic2 + 0.25, det = a*c - b*b
-//   q2 = (rcp, colR, colG, colB)   rcp = Newton-refined 1/det (0 when det is outside the safe range),
+//   q2 = (rcp, colR, colG, colB)   rcp = correctly rounded 1/det,
 //                                  col = SH_0 * rgb
 enum RecSlot {
     R_U = 0, R_V = 1, R_R2 = 2, R_OPA = 3,

@@ -53,17 +53,10 @@ __device__ __forceinline__ void make_record(float u, float v, float c0, float c1
     const float c = __fadd_rn(c2, 0.25f);
     const float bh = __fmul_rn(c1, 0.5f);
     const float det = __fmaf_rn(a, c, -__fmul_rn(bh, bh));
-    // 1/det refined by one Newton step: with it, q = num*rcp; q += rcp*fma(-det,q,num) is the correctly
-    // rounded IEEE quotient num/det (the fast path of the compiler's own division), valid while det and
-    // num stay far from the denormal/overflow range; rcp = 0 tells the kernel to use __fdiv_rn instead.
-    float rcp = 0.0f;
-    const float adet = fabsf(det);
-    if (adet > 1e-18f && adet < 1e18f) {
-        float r0;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(det));
-        const float e = __fmaf_rn(-det, r0, 1.0f);
-        rcp = __fmaf_rn(r0, e, r0);
-    }
+    // 1/det, correctly rounded.  The forward uses it for q = num*rcp; q += rcp*fma(-det,q,num), which is the
+    // correctly rounded IEEE quotient num/det while det and num stay far from the denormal/overflow range
+    // (Markstein); the backward uses it as the reference's `1.0 / det` (src/render_backward.cu:153).
+    const float rcp = __frcp_rn(det);
     rec[R_U] = u;
     rec[R_V] = v;
     rec[R_R2] = cull_tau(a, bh, c, det, opa);
