@@ -565,15 +565,24 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
     const float* g_opa = g_rgb + (size_t)N * 3;
     const float* g_uv = g_opa + (size_t)N;
     const float* g_conic = g_uv + (size_t)N * 2;
-    int n_rest = 0;
+    const int n_rest = sh_rest.has_value() ? (int)sh_rest->size(2) : 0;
+    // All parameter gradients of a view live in ONE allocation, [xyz 3N | quaternion 4N | scale 3N |
+    // opacity N | rgb 3N | sh 3*n_rest*N], every section starting on a 16-byte boundary (TMA bulk stores):
+    // a trainer that sums gradients over views / ranks reduces that one buffer (view_parallel.py).
+    const int64_t widths[6] = {3, 4, 3, 1, 3, 3 * (int64_t)n_rest};
+    int64_t offs[7];
+    offs[0] = 0;
+    for (int i = 0; i < 6; ++i) offs[i + 1] = (offs[i] + N * widths[i] + 3) & ~(int64_t)3;
+    torch::Tensor flat = torch::empty({offs[6]}, opt);
+    for (int i = 0; i < 6; ++i)  // padding between sections (only when N is not a multiple of 4)
+        if (offs[i + 1] > offs[i] + N * widths[i]) flat.narrow(0, offs[i] + N * widths[i], offs[i + 1] - offs[i] - N * widths[i]).zero_();
+    auto section = [&](int i, std::vector<int64_t> shape) {
+        return flat.narrow(0, offs[i], N * widths[i]).view(shape);
+    };
+    torch::Tensor o_xyz = section(0, {N, 3}), o_q = section(1, {N, 4}), o_s = section(2, {N, 3}),
+                  o_o = section(3, {N}), o_dc = section(4, {N, 3});
     torch::Tensor g_sh;
-    if (sh_rest.has_value()) {
-        n_rest = sh_rest->size(2);
-        g_sh = torch::empty_like(*sh_rest);
-    }
-    torch::Tensor o_xyz = torch::empty_like(xyz), o_q = torch::empty_like(quaternion),
-                  o_s = torch::empty_like(scale), o_o = torch::empty_like(opacity_logit),
-                  o_dc = torch::empty({N, 3}, opt);
+    if (n_rest) g_sh = section(5, {N, 3, (int64_t)n_rest});
     check_rc(gsr_preprocess_backward((int)N, n_rest, F32PTR(xyz), F32PTR(quaternion), F32PTR(scale),
                                      F32PTR(opacity_logit), F32PTR(camera_T_world), F32PTR(K),
                                      camera_centre.has_value() ? camera_centre->data_ptr<float>() : nullptr,
@@ -583,6 +592,7 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
              "gsr_preprocess_backward");
     std::vector<torch::Tensor> out = {o_xyz, o_q, o_s, o_o, o_dc};
     if (n_rest) out.push_back(g_sh);
+    out.push_back(flat);  // last: the allocation all the others are views of
     return out;
 }
 

@@ -66,10 +66,11 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
-                 "n_per_pixel", "w_per_pixel", "background", "profile")
+                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat")
 
     def __init__(self, profile=None):
         self.profile = profile  # optional list: (stage name, start event, end event) per native call
+        self.grad_flat = None   # set by the backward pass: flat buffer holding all parameter gradients
 
 
 class _stage:
@@ -149,6 +150,7 @@ class _ProjectGaussians(torch.autograd.Function):
                                                        camera_T_world, K, centre, st.visible)
         g_xyz, g_q, g_s, g_o, g_dc = grads[:5]
         g_sh = grads[5] if ctx.has_sh else None
+        st.grad_flat = grads[-1]  # the one allocation all parameter gradients of this view are views of
         return g_xyz, g_q, g_s, g_o.view(-1, 1), g_dc, g_sh, None, None, None, None
 
 

@@ -48,3 +48,65 @@ def test_view_sharding_two_ranks():
     assert all(s > 0 for s in slots)                       # every (step, rank) slot rendered once
     assert [s - 1 for s in slots] == [k % n_poses for k in range(steps * world)]  # consecutive views, no overlap
     assert ms == 15.0                                      # max over ranks
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gaussian_splatting_b200.view_parallel import GradientBucket, all_reduce_statistics, views_of_rank
+
+        torch.manual_seed(0)  # same parameters on every rank (replicated Gaussians)
+        params = [torch.randn(7, 3, requires_grad=True), torch.randn(7, 1, requires_grad=True),
+                  torch.randn(7, 3, 15, requires_grad=True)]
+        # (1) attach mode: .grad are views of one flat buffer, autograd accumulates in place
+        bucket = GradientBucket(params).attach()
+        bucket.zero()
+        w = float(views_of_rank(0, rank, world, 8) + 1)  # a per-rank "view": loss = w * sum(p^2)
+        loss = sum((p * p).sum() for p in params) * w
+        loss.backward()
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, bucket.views))
+        bucket.all_reduce(average=True)
+        mean_w = sum(views_of_rank(0, r, world, 8) + 1 for r in range(world)) / world
+        err_attach = max(float((p.grad - 2 * mean_w * p.detach()).abs().max()) for p in params)
+        # (2) adopt mode: gradients already live in one allocation (what the fused backward leaves behind)
+        flat = torch.empty(sum(p.numel() for p in params))
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view(p.shape)
+            p.grad.copy_(2 * w * p.detach())
+            off += p.numel()
+        b2 = GradientBucket.adopt(flat, params)
+        assert b2.zero_copy
+        b2.all_reduce(average=False)
+        sum_w = sum(views_of_rank(0, r, world, 8) + 1 for r in range(world))
+        err_adopt = max(float((p.grad - 2 * sum_w * p.detach()).abs().max()) for p in params)
+        # (3) gradients somewhere else -> flatten copy
+        for p in params:
+            p.grad = (2 * w * p.detach()).clone()
+        b3 = GradientBucket.adopt(flat, params)
+        assert not b3.zero_copy
+        b3.all_reduce(average=False)
+        err_copy = max(float((p.grad - 2 * sum_w * p.detach()).abs().max()) for p in params)
+        stats = torch.full((7, 2), float(rank + 1))
+        all_reduce_statistics([stats])
+        if rank == 0:
+            out.put((err_attach, err_adopt, err_copy, float(stats[0, 0])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_bucket_all_reduce_two_ranks():
+    """view_parallel.GradientBucket: one flat all-reduce of the parameter gradients (attach / adopt / copy)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    err_attach, err_adopt, err_copy, stat = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err_attach < 1e-5 and err_adopt < 1e-5 and err_copy < 1e-5
+    assert stat == 3.0  # 1 + 2

@@ -1,0 +1,139 @@
+"""View-parallel optimisation step on N GPUs of one node (second half):
+
+    rank r:  render view (step*N + r)  ->  L1 loss against its target  ->  backward
+    all:     ONE all-reduce (NCCL, average) of the flat gradient bucket the fused backward produced
+    all:     Adam step on the replicated Gaussians (identical on every rank)
+
+Launch:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+             --master-port P tools/e2e/view_parallel_step.py --gaussians 3000000 --res 1080p --steps 10
+(or plain `python tools/e2e/view_parallel_step.py` for N = 1: the collective is skipped).
+
+Prints one JSON line from rank 0 with CUDA-event times (max over ranks) of the three phases and of the whole
+step, the bytes reduced, whether the bucket was zero-copy, and a consistency check (parameters identical on
+all ranks after the steps).  Targets are renders of a perturbed copy of the scene, so the loss decreases; the
+LR convention is the reference's (1 view per optimizer step -> here the MEAN gradient of N views per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gaussians", type=int, default=3_000_000)
+    ap.add_argument("--res", default="1080p")
+    ap.add_argument("--sh-degree", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--views", type=int, default=8)
+    ap.add_argument("--lr", type=float, default=2e-3, help="base learning rate (reference: 0.002)")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gaussian_splatting_b200 import synth
+    from gaussian_splatting_b200.rasterize import rasterize
+    from gaussian_splatting_b200.view_parallel import PARAM_FIELDS, GradientBucket, broadcast_parameters, views_of_rank
+
+    g = synth.make_gaussians(a.gaussians, a.res, sh_degree=a.sh_degree, seed=0, device=dev, requires_grad=True)
+    broadcast_parameters(g)  # identical bits everywhere (they already are: same seed)
+    cam = synth.make_camera(a.res, device=dev)
+    bg = torch.full((3,), 0.5, device=dev)
+    params = [getattr(g, f) for f in PARAM_FIELDS if getattr(g, f, None) is not None]
+    # learning-rate multipliers of the reference's optimizer (splat_py/config.py: xyz 0.1, quaternion 2, scale 5,
+    # opacity 10, rgb 2, sh 0.1 times base_lr)
+    mult = dict(xyz=0.1, quaternion=2.0, scale=5.0, opacity=10.0, rgb=2.0, sh=0.1)
+    opt = torch.optim.Adam([dict(params=[getattr(g, f)], lr=a.lr * mult[f]) for f in PARAM_FIELDS
+                            if getattr(g, f, None) is not None], fused=True)
+
+    # targets: the same scene with brighter colours, rendered once per view
+    poses = [synth.make_pose(v, a.views, device=dev) for v in range(a.views)]
+    with torch.no_grad():
+        g.rgb.mul_(1.15)
+        targets = [rasterize(g, T, cam, 0.3, 500.0, 100, 3.0, True, bg)[0].clone() for T in poses]
+        g.rgb.div_(1.15)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    t_render, t_reduce, t_adam, t_step, losses = [], [], [], [], []
+    zero_copy = None
+    for it in range(a.warmup + a.steps):
+        v = views_of_rank(it, rank, world, a.views)
+        for p in params:
+            p.grad = None
+        e = [ev() for _ in range(4)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e[0].record()
+        image, _, _, state = rasterize(g, poses[v], cam, 0.3, 500.0, 100, 3.0, True, bg, return_state=True)
+        loss = (image - targets[v]).abs().mean()
+        loss.backward()
+        e[1].record()
+        bucket = GradientBucket.adopt(state.grad_flat, params)
+        bucket.all_reduce(average=True)
+        e[2].record()
+        opt.step()
+        e[3].record()
+        torch.cuda.synchronize()
+        zero_copy = bucket.zero_copy
+        if it >= a.warmup:
+            t_render.append(e[0].elapsed_time(e[1]))
+            t_reduce.append(e[1].elapsed_time(e[2]))
+            t_adam.append(e[2].elapsed_time(e[3]))
+            t_step.append(e[0].elapsed_time(e[3]))
+            losses.append(float(loss))
+
+    def reduce_max(xs):
+        t = torch.tensor([sum(xs) / len(xs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # replicas must still be identical: compare a checksum of the parameters across ranks
+    chk = torch.stack([p.detach().double().sum() for p in params])
+    same = True
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool((lo == hi).all())
+    mean_loss = torch.tensor([losses[0], losses[-1]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(mean_loss)
+        mean_loss /= world
+    line = {
+        "what": "view-parallel step: render fwd+bwd of one view per GPU, one all-reduce of the gradient bucket, fused Adam",
+        "n_gpus": world, "gaussians": a.gaussians, "res": a.res, "sh_degree": a.sh_degree, "steps": a.steps,
+        "ms_render_fwd_bwd": round(reduce_max(t_render), 3), "ms_all_reduce": round(reduce_max(t_reduce), 3),
+        "ms_adam": round(reduce_max(t_adam), 3), "ms_step": round(reduce_max(t_step), 3),
+        "views_per_second": round(world * 1e3 / reduce_max(t_step), 1),
+        "bucket_bytes": bucket.nbytes(), "bucket_zero_copy": bool(zero_copy),
+        "replicas_identical_after_steps": same,
+        "loss_first_last": [round(float(mean_loss[0]), 6), round(float(mean_loss[1]), 6)],
+        "device": torch.cuda.get_device_name(local),
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
