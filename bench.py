@@ -302,7 +302,7 @@ def run_b200(args, rank, world, local):
         "gpu_launches": len(MY_KERNELS) * args.steps, "kernels": MY_KERNELS,
         "roofline": roofline, "cpu_baseline": cpu, "impl": "b200",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_leg(args, rows=48):
@@ -453,7 +453,7 @@ def run_reference(args, rank, world, local):
                                    "(no CPU implementation exists); see --impl reference-cpu for the CPU port"},
         "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_reference_cpu(args, rank):
@@ -468,10 +468,31 @@ def run_reference_cpu(args, rank):
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version line to
+    stdout at NCCL_DEBUG >= VERSION, ninja / torch extensions chatter): keep the real stdout aside and point
+    file descriptor 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

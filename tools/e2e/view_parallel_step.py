@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--lr", type=float, default=2e-3, help="base learning rate (reference: 0.002)")
     a = ap.parse_args()
 
+    real_stdout = os.fdopen(os.dup(1), "w")  # NCCL prints its version line on stdout: keep ours clean
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -130,7 +132,8 @@ def main():
         "device": torch.cuda.get_device_name(local),
     }
     if rank == 0:
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
