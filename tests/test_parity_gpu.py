@@ -264,6 +264,44 @@ def test_live_reference_100k_720p(pose):
 
 
 @needs_ref
+def test_live_reference_exact_arithmetic_paths():
+    """Scene built to hit the forward kernel's rare exact paths: splats whose centre falls
+    EXACTLY on a pixel centre (numerator 0, outside the hoisted-reciprocal division's proven range) and splats
+    whose 2-D covariance determinant exceeds 1e18 (record marked unsafe) — the flagged pixels are recomputed by
+    render_pixel_exact_warp.  Everything must still match the compiled reference bit for bit."""
+    ref_loader.load_reference()
+    ref_ras = sys.modules["splat_py_ref.rasterize"]
+    ref_structs = sys.modules["splat_py_ref.structs"]
+    rng = np.random.default_rng(7)
+    sc = scenes.np_scene(3000, "tiny", sh_degree=0, seed=3, sigma_px=(2.0, 0.5, 0.5, 8.0))
+    sc["K"] = np.array([[64, 0, 32], [0, 64, 32], [0, 0, 1]], np.float32)  # powers of two: u = 64*x/z + 32 is exact
+    sc["T"] = np.eye(4, dtype=np.float32)
+    n_exact, n_huge = 300, 12
+    z = np.full(n_exact, 2.0, np.float32)
+    px, py = rng.integers(0, 64, n_exact), rng.integers(0, 64, n_exact)
+    sc["xyz"][:n_exact] = np.stack([(px - 32) / 64.0 * z, (py - 32) / 64.0 * z, z], 1).astype(np.float32)
+    sc["xyz"][n_exact:n_exact + n_huge, 2] = 2.0
+    sc["scale"][n_exact:n_exact + n_huge] = 7.5       # exp(7.5) = 1808 world units -> det(Sigma_2D) ~ 1e19
+    sc["opacity"][n_exact:n_exact + n_huge] = -3.0
+    G = synth.make_upstream_grad("tiny").numpy()
+    mine = run_b200(sc, G=G)
+    g = gaussians_from(sc)
+    gr = ref_structs.Gaussians(g.xyz, g.rgb, g.opacity, g.scale, g.quaternion, g.sh)
+    image, mask, uv = ref_ras.rasterize(gr, to_t(sc["T"]), ref_structs.Camera(64, 64, to_t(sc["K"])), 0.3, 500.0, 100, 3.0,
+                                        True, torch.full((3,), 0.5, device=dev()))
+    uv.retain_grad()
+    image.backward(to_t(G))
+    uvn = uv.detach().cpu().numpy()
+    assert int(((uvn == np.round(uvn)).all(1)).sum()) >= n_exact // 2   # the exact-centre splats survived culling
+    assert_bits_equal(mine["culling_mask"], mask, "culling_mask")
+    assert_bits_equal(mine["uv"], uv, "uv")
+    assert_bits_equal(mine["image"], image, "image")
+    for k, v in dict(g_xyz=g.xyz.grad, g_rgb=g.rgb.grad, g_opacity=g.opacity.grad, g_scale=g.scale.grad,
+                     g_quaternion=g.quaternion.grad, g_uv=uv.grad).items():
+        assert rel(mine[k], v) < REL_TOL, (k, rel(mine[k], v))
+
+
+@needs_ref
 def test_reference_python_runs_on_this_library():
     """Drop-in proof: the reference's own splat_py.rasterize on THIS library's `splat_cuda`."""
     ref_loader.load_reference_on_b200()
