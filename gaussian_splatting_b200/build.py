@@ -28,12 +28,14 @@ CU_SOURCES = [
     "gsr_binning.cu",
     "gsr_render.cu",
     "gsr_render_generic.cu",
+    "gsr_adam.cu",
 ]
 HEADERS = [
     CSRC / "gsr_common.cuh",
     CSRC / "gsr_math.cuh",
     CSRC / "gsr_math_bwd.cuh",
     CSRC / "gsr_record.cuh",
+    CSRC / "gsr_f32x2.cuh",
     ROOT / "include" / "gsr_b200.h",
 ]
 

@@ -555,7 +555,8 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
                                                      c10::optional<torch::Tensor> sh_rest,
                                                      torch::Tensor camera_T_world, torch::Tensor K,
                                                      c10::optional<torch::Tensor> camera_centre,
-                                                     torch::Tensor visible) {
+                                                     torch::Tensor visible,
+                                                     c10::optional<torch::Tensor> out_flat) {
     CHECK_VALID_INPUT(slab); CHECK_FLOAT_TENSOR(slab);
     const int64_t N = xyz.size(0);
     TORCH_CHECK(slab.numel() == N * 9, "gradient slab must hold 9 floats per gaussian");
@@ -573,7 +574,16 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
     int64_t offs[7];
     offs[0] = 0;
     for (int i = 0; i < 6; ++i) offs[i + 1] = (offs[i] + N * widths[i] + 3) & ~(int64_t)3;
-    torch::Tensor flat = torch::empty({offs[6]}, opt);
+    // out_flat: a caller-owned buffer of the same layout (e.g. symmetric memory peers can read, view_parallel.py)
+    torch::Tensor flat;
+    if (out_flat.has_value()) {
+        flat = *out_flat;
+        CHECK_VALID_INPUT(flat); CHECK_FLOAT_TENSOR(flat);
+        TORCH_CHECK(flat.numel() == offs[6], "out_flat must hold ", offs[6], " floats");
+        TORCH_CHECK((reinterpret_cast<uintptr_t>(flat.data_ptr()) & 15u) == 0, "out_flat must be 16-byte aligned");
+    } else {
+        flat = torch::empty({offs[6]}, opt);
+    }
     for (int i = 0; i < 6; ++i)  // padding between sections (only when N is not a multiple of 4)
         if (offs[i + 1] > offs[i] + N * widths[i]) flat.narrow(0, offs[i] + N * widths[i], offs[i + 1] - offs[i] - N * widths[i]).zero_();
     auto section = [&](int i, std::vector<int64_t> shape) {
@@ -594,6 +604,54 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
     if (n_rest) out.push_back(g_sh);
     out.push_back(flat);  // last: the allocation all the others are views of
     return out;
+}
+
+// sizes of the flat parameter / gradient layout: exclusive end of each section, in elements
+std::vector<int64_t> flat_section_ends(int64_t N, int64_t n_sh_rest) {
+    const int64_t widths[6] = {3, 4, 3, 1, 3, 3 * n_sh_rest};
+    std::vector<int64_t> ends;
+    int64_t off = 0;
+    for (int i = 0; i < 6; ++i) {
+        off = (off + N * widths[i] + 3) & ~(int64_t)3;
+        if (widths[i] > 0) ends.push_back(off);
+    }
+    return ends;
+}
+
+void adam_step_flat(torch::Tensor p, torch::Tensor g, torch::Tensor m, torch::Tensor v,
+                    std::vector<int64_t> section_end, std::vector<double> section_lr, double beta1, double beta2,
+                    double eps, int64_t step) {
+    CHECK_VALID_INPUT(p); CHECK_VALID_INPUT(g); CHECK_VALID_INPUT(m); CHECK_VALID_INPUT(v);
+    CHECK_FLOAT_TENSOR(p); CHECK_FLOAT_TENSOR(g); CHECK_FLOAT_TENSOR(m); CHECK_FLOAT_TENSOR(v);
+    const int64_t n = p.numel();
+    TORCH_CHECK(g.numel() == n && m.numel() == n && v.numel() == n, "p, g, m, v must have the same length");
+    TORCH_CHECK(section_end.size() == section_lr.size() && !section_end.empty() && section_end.back() == n,
+                "sections must cover the buffer");
+    c10::cuda::CUDAGuard guard(p.device());
+    check_rc(gsr_adam_step(n, F32PTR(p), F32PTR(g), F32PTR(m), F32PTR(v), (int)section_end.size(),
+                           section_end.data(), section_lr.data(), beta1, beta2, eps, (int)step, cur_stream()),
+             "gsr_adam_step");
+}
+
+void adam_step_sharded(int64_t lo, int64_t hi, std::vector<int64_t> peer_grad_ptrs,
+                       std::vector<int64_t> peer_param_ptrs, int64_t self_rank, torch::Tensor m_shard,
+                       torch::Tensor v_shard, std::vector<int64_t> section_end, std::vector<double> section_lr,
+                       double beta1, double beta2, double eps, int64_t step) {
+    CHECK_VALID_INPUT(m_shard); CHECK_VALID_INPUT(v_shard); CHECK_FLOAT_TENSOR(m_shard); CHECK_FLOAT_TENSOR(v_shard);
+    TORCH_CHECK(peer_grad_ptrs.size() == peer_param_ptrs.size() && !peer_grad_ptrs.empty(), "one pointer per rank");
+    TORCH_CHECK(m_shard.numel() == hi - lo && v_shard.numel() == hi - lo, "state shards must hold hi - lo elements");
+    TORCH_CHECK(section_end.size() == section_lr.size() && !section_end.empty(), "bad sections");
+    std::vector<const float*> gp;
+    std::vector<float*> pp;
+    for (size_t q = 0; q < peer_grad_ptrs.size(); ++q) {
+        gp.push_back(reinterpret_cast<const float*>(peer_grad_ptrs[q]));
+        pp.push_back(reinterpret_cast<float*>(peer_param_ptrs[q]));
+    }
+    c10::cuda::CUDAGuard guard(m_shard.device());
+    check_rc(gsr_adam_step_sharded(lo, hi, (int)gp.size(), gp.data(), pp.data(), (int)self_rank, F32PTR(m_shard),
+                                   F32PTR(v_shard), (int)section_end.size(), section_end.data(), section_lr.data(),
+                                   beta1, beta2, eps, (int)step, cur_stream()),
+             "gsr_adam_step_sharded");
 }
 
 std::string version() { return gsr_version(); }
@@ -627,5 +685,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("fused_render_forward", &fused_render_forward, "tile renderer forward on a record stream");
     m.def("fused_render_backward", &fused_render_backward, "tile renderer backward -> per-gaussian gradient slab");
     m.def("fused_preprocess_backward", &fused_preprocess_backward, "fused per-gaussian backward");
+    m.def("flat_section_ends", &flat_section_ends, "section ends of the flat parameter/gradient layout");
+    m.def("adam_step_flat", &adam_step_flat, "Adam on the flat parameter buffer");
+    m.def("adam_step_sharded", &adam_step_sharded, "reduce-scatter + Adam + all-gather over peer memory");
     m.def("version", &version, "library version string");
 }

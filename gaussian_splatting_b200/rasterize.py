@@ -66,11 +66,12 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
-                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat")
+                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out")
 
     def __init__(self, profile=None):
         self.profile = profile  # optional list: (stage name, start event, end event) per native call
         self.grad_flat = None   # set by the backward pass: flat buffer holding all parameter gradients
+        self.grad_out = None    # optional caller-owned buffer (same layout) the backward writes them into
 
 
 class _stage:
@@ -147,7 +148,7 @@ class _ProjectGaussians(torch.autograd.Function):
             slab[4 * N:6 * N].view(N, 2).index_copy_(0, st.vis_idx, grad_uv.contiguous())
         with _stage(st, "preprocess_bwd"):
             grads = native().fused_preprocess_backward(slab, xyz, quaternion, scale, opacity_flat, sh,
-                                                       camera_T_world, K, centre, st.visible)
+                                                       camera_T_world, K, centre, st.visible, st.grad_out)
         g_xyz, g_q, g_s, g_o, g_dc = grads[:5]
         g_sh = grads[5] if ctx.has_sh else None
         st.grad_flat = grads[-1]  # the one allocation all parameter gradients of this view are views of
@@ -176,13 +177,14 @@ class _CompositeTiles(torch.autograd.Function):
 
 
 def rasterize(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist,
-              use_sh_precompute, background_rgb, return_state=False, profile=None):
+              use_sh_precompute, background_rgb, return_state=False, profile=None, grad_out=None):
     if gaussians.sh is not None and not use_sh_precompute:
         return rasterize_unfused(gaussians, camera_T_world, camera, near_thresh, far_thresh,
                                  cull_mask_padding, mh_dist, use_sh_precompute, background_rgb)
     if gaussians.xyz.dtype != torch.float32:
         raise TypeError("the fused rasterizer is fp32; use rasterize_unfused for float64 inputs")
     state = _ViewState(profile)
+    state.grad_out = grad_out
     cfg = (int(camera.height), int(camera.width), float(near_thresh), float(far_thresh),
            float(cull_mask_padding), float(mh_dist))
     uv, carrier = _ProjectGaussians.apply(

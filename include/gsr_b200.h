@@ -232,6 +232,28 @@ int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float*
                             float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
                             float* g_rgb_dc, float* g_sh_rest, void* stream);
 
+/* ---- optimizer step on the flat parameter buffer ----------------------------
+ * Replaces torch.optim.Adam.step() as configured by splat_py/optimizer_manager.py:13-44 (one parameter group
+ * per field, betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad), with the per-element operation order
+ * of torch's CUDA implementation.  p, g, m, v: flat fp32 arrays of n elements laid out like the gradients
+ * gsr_preprocess_backward produces ([xyz|quaternion|scale|opacity|rgb|sh], sections 16-byte aligned; n and
+ * every section_end are multiples of 4).  section_end[k] = exclusive end (in elements) of section k,
+ * section_lr[k] its learning rate; step = 1 for the first update. */
+int gsr_adam_step(int64_t n, float* p, const float* g, float* m, float* v, int n_sections,
+                  const int64_t* section_end, const double* section_lr, double beta1, double beta2, double eps, int step,
+                  void* stream);
+
+/* View-parallel form, one process per GPU: this rank owns elements [lo, hi) of the flat buffer.  The gradient
+ * of the range is read from every rank's gradient buffer (peer_grads[q], device pointers valid on this device:
+ * CUDA IPC / symmetric memory over NVLink), summed in rank order and divided by world; m_shard / v_shard hold
+ * only the owned range (hi - lo elements); the updated parameters are stored into every rank's parameter
+ * buffer (peer_params[q]).  Reduce-scatter + Adam + all-gather in one kernel.  The caller provides the
+ * cross-rank ordering: all gradients complete before the launch, a barrier after it before parameters are read. */
+int gsr_adam_step_sharded(int64_t lo, int64_t hi, int world, const float* const* peer_grads,
+                          float* const* peer_params, int self_rank, float* m_shard, float* v_shard, int n_sections,
+                          const int64_t* section_end, const double* section_lr, double beta1, double beta2, double eps,
+                          int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--lr", type=float, default=2e-3, help="base learning rate (reference: 0.002)")
+    ap.add_argument("--stages", action="store_true", help="also report the rasterizer's per-stage times of the last step")
+    ap.add_argument("--optimizer", choices=["torch", "flat", "sharded"], default="torch",
+                    help="torch: NCCL all-reduce + torch.optim.Adam(fused); flat: NCCL all-reduce + gsr_adam_step on the "
+                         "flat buffer; sharded: ONE kernel per rank doing reduce-scatter + Adam + all-gather over "
+                         "NVLink peer memory (symmetric memory), optimizer state sharded")
     a = ap.parse_args()
 
     real_stdout = os.fdopen(os.dup(1), "w")  # NCCL prints its version line on stdout: keep ours clean
@@ -58,12 +63,31 @@ def main():
     broadcast_parameters(g)  # identical bits everywhere (they already are: same seed)
     cam = synth.make_camera(a.res, device=dev)
     bg = torch.full((3,), 0.5, device=dev)
-    params = [getattr(g, f) for f in PARAM_FIELDS if getattr(g, f, None) is not None]
     # learning-rate multipliers of the reference's optimizer (splat_py/config.py: xyz 0.1, quaternion 2, scale 5,
     # opacity 10, rgb 2, sh 0.1 times base_lr)
-    mult = dict(xyz=0.1, quaternion=2.0, scale=5.0, opacity=10.0, rgb=2.0, sh=0.1)
-    opt = torch.optim.Adam([dict(params=[getattr(g, f)], lr=a.lr * mult[f]) for f in PARAM_FIELDS
-                            if getattr(g, f, None) is not None], fused=True)
+    from gaussian_splatting_b200.flat_adam import REFERENCE_LR_MULTIPLIERS as mult, FlatAdam, ShardedFlatAdam, flatten_gaussians
+
+    grads_sym = None
+    if a.optimizer == "torch":
+        opt = torch.optim.Adam([dict(params=[getattr(g, f)], lr=a.lr * mult[f]) for f in PARAM_FIELDS
+                                if getattr(g, f, None) is not None], fused=True)
+    elif a.optimizer == "flat":
+        flat, ends, names = flatten_gaussians(g)
+        opt = FlatAdam(flat, ends, [a.lr * mult[f] for f in names])
+    else:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        assert world > 1, "--optimizer sharded needs torchrun with at least 2 ranks"
+        n_rest = 0 if g.sh is None else g.sh.shape[2]
+        from gaussian_splatting_b200.flat_adam import section_ends
+
+        total = section_ends(a.gaussians, n_rest)[-1]
+        params_sym = symm_mem.empty(total, dtype=torch.float32, device=dev)
+        grads_sym = symm_mem.empty(total, dtype=torch.float32, device=dev)
+        grads_sym.zero_()
+        flat, ends, names = flatten_gaussians(g, flat=params_sym)
+        opt = ShardedFlatAdam(params_sym, grads_sym, ends, [a.lr * mult[f] for f in names])
+    params = [getattr(g, f) for f in PARAM_FIELDS if getattr(g, f, None) is not None]
 
     # targets: the same scene with brighter colours, rendered once per view
     poses = [synth.make_pose(v, a.views, device=dev) for v in range(a.views)]
@@ -84,17 +108,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         e[0].record()
-        image, _, _, state = rasterize(g, poses[v], cam, 0.3, 500.0, 100, 3.0, True, bg, return_state=True)
+        prof = [] if (a.stages and it == a.warmup + a.steps - 1) else None
+        image, _, _, state = rasterize(g, poses[v], cam, 0.3, 500.0, 100, 3.0, True, bg, return_state=True,
+                                       grad_out=grads_sym, profile=prof)
         loss = (image - targets[v]).abs().mean()
         loss.backward()
         e[1].record()
-        bucket = GradientBucket.adopt(state.grad_flat, params)
-        bucket.all_reduce(average=True)
-        e[2].record()
-        opt.step()
+        if a.optimizer == "sharded":
+            e[2].record()
+            opt.step()  # barrier, reduce-scatter + Adam + all-gather in one kernel, barrier
+            bucket_bytes, zero_copy = grads_sym.numel() * 4, True
+        else:
+            bucket = GradientBucket.adopt(state.grad_flat, params)
+            bucket.all_reduce(average=True)
+            e[2].record()
+            if a.optimizer == "flat":
+                opt.step(bucket.flat)
+            else:
+                opt.step()
+            bucket_bytes, zero_copy = bucket.nbytes(), bucket.zero_copy
         e[3].record()
         torch.cuda.synchronize()
-        zero_copy = bucket.zero_copy
+        if prof is not None:
+            stage_ms = {name: round(e0.elapsed_time(e1), 3) for name, e0, e1 in prof}
         if it >= a.warmup:
             t_render.append(e[0].elapsed_time(e[1]))
             t_reduce.append(e[1].elapsed_time(e[2]))
@@ -124,13 +160,15 @@ def main():
         "what": "view-parallel step: render fwd+bwd of one view per GPU, one all-reduce of the gradient bucket, fused Adam",
         "n_gpus": world, "gaussians": a.gaussians, "res": a.res, "sh_degree": a.sh_degree, "steps": a.steps,
         "ms_render_fwd_bwd": round(reduce_max(t_render), 3), "ms_all_reduce": round(reduce_max(t_reduce), 3),
-        "ms_adam": round(reduce_max(t_adam), 3), "ms_step": round(reduce_max(t_step), 3),
+        "ms_optimizer": round(reduce_max(t_adam), 3), "ms_step": round(reduce_max(t_step), 3),
         "views_per_second": round(world * 1e3 / reduce_max(t_step), 1),
-        "bucket_bytes": bucket.nbytes(), "bucket_zero_copy": bool(zero_copy),
+        "optimizer": a.optimizer, "bucket_bytes": bucket_bytes, "bucket_zero_copy": bool(zero_copy),
         "replicas_identical_after_steps": same,
         "loss_first_last": [round(float(mean_loss[0]), 6), round(float(mean_loss[1]), 6)],
         "device": torch.cuda.get_device_name(local),
     }
+    if a.stages:
+        line["stage_ms_rank0_last_step"] = stage_ms
     if rank == 0:
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
