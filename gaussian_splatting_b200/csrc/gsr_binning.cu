@@ -19,9 +19,12 @@ constexpr int BIN_THREADS = 256;
 
 // tiles overlapped by one gaussian.  Reference: src/tile_culling.cu:139-176.
 // When keys != nullptr also emits the pairs at keys[base...].
+// id_bits > 0: the gaussian id is packed into the low id_bits of the key, (tile | depth | id), and no ids
+// array is written (keys-only sort); id_bits == 0: key = (tile | depth), ids[] holds the gaussian id.
 __device__ __forceinline__ int walk_tiles(const Obb& o, float u, float v, int ntx, int nty,
                                           uint32_t zkey, uint32_t id, uint64_t* __restrict__ keys,
-                                          uint32_t* __restrict__ ids, int64_t base, int depth_bits = 32) {
+                                          uint32_t* __restrict__ ids, int64_t base, int depth_bits = 32,
+                                          int id_bits = 0) {
     int x0, x1, y0, y1;
     tile_window(u, v, o.radius_tiles, ntx, nty, x0, x1, y0, y1);
     int n = 0;
@@ -34,8 +37,13 @@ __device__ __forceinline__ int walk_tiles(const Obb& o, float u, float v, int nt
             if (obb_hits_tile(o, left, right, top, bottom)) {
                 if (keys) {
                     const uint32_t tile = (uint32_t)(ty * ntx + tx);
-                    keys[base + n] = ((uint64_t)tile << depth_bits) | zkey;
-                    ids[base + n] = id;
+                    const uint64_t k = ((uint64_t)tile << depth_bits) | zkey;
+                    if (id_bits > 0) {
+                        keys[base + n] = (k << id_bits) | id;
+                    } else {
+                        keys[base + n] = k;
+                        ids[base + n] = id;
+                    }
                 }
                 ++n;
             }
@@ -76,7 +84,7 @@ __global__ void __launch_bounds__(BIN_THREADS)
     k_emit_pairs_fused(int N, const float* __restrict__ records,
                        const uint32_t* __restrict__ zkey, const uint8_t* __restrict__ visible,
                        const uint64_t* __restrict__ scan, int ntx, int nty, float mh, int depth_bits,
-                       uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
+                       int id_bits, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
                        int32_t* __restrict__ vis_idx, float* __restrict__ uv_compact) {
     const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
     if (i >= N) return;
@@ -93,7 +101,8 @@ __global__ void __launch_bounds__(BIN_THREADS)
     Obb o;
     const float* r = records + (size_t)i * REC;
     compute_obb(u, v, r[R_A], __fmul_rn(r[R_B2], 0.5f), r[R_C], mh, o);
-    walk_tiles(o, u, v, ntx, nty, zkey[i], (uint32_t)i, keys, ids, (int64_t)(prev & 0xffffffffu), depth_bits);
+    walk_tiles(o, u, v, ntx, nty, zkey[i], (uint32_t)i, keys, ids, (int64_t)(prev & 0xffffffffu), depth_bits,
+               id_bits);
 }
 
 // tile_ranges[t] = first sorted position whose tile id >= t  (ranges[n_tiles] = P).
@@ -135,6 +144,19 @@ __global__ void __launch_bounds__(BIN_THREADS)
     if (t >= (int64_t)P * 3) return;
     const int p = (int)(t / 3), lane = (int)(t % 3);
     out[t] = __ldg(rec + (size_t)ids[p] * 3 + lane);
+}
+
+// same, ids taken from the low id_bits of the sorted keys; also writes them out for the backward's flush
+__global__ void __launch_bounds__(BIN_THREADS)
+    k_gather_records_keys(int P, const uint64_t* __restrict__ keys, uint64_t id_mask,
+                          const float4* __restrict__ rec, float4* __restrict__ out,
+                          int32_t* __restrict__ ids_out) {
+    const int64_t t = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (t >= (int64_t)P * 3) return;
+    const int p = (int)(t / 3), lane = (int)(t % 3);
+    const uint32_t id = (uint32_t)(keys[p] & id_mask);
+    if (lane == 0) ids_out[p] = (int32_t)id;
+    out[t] = __ldg(rec + (size_t)id * 3 + lane);
 }
 
 __global__ void __launch_bounds__(BIN_THREADS)
@@ -250,8 +272,52 @@ int gsr_emit_pairs(int N, const float* records, const uint32_t* depth_key,
                    uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
-    k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, depth_bits, keys,
+    k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, depth_bits, 0, keys,
                                      ids, vis_idx, uv_compact);
+    return (int)cudaGetLastError();
+}
+
+// ---- keys-only variant: (tile | depth | gaussian id) in one 64-bit key -------------------------------
+int gsr_packed_id_bits(int N, int n_tiles, int depth_bits) {
+    int id_bits = 1;
+    while (((int64_t)1 << id_bits) < (int64_t)N) ++id_bits;
+    return (sort_end_bit(n_tiles, depth_bits) + id_bits <= 64) ? id_bits : 0;
+}
+
+int gsr_emit_keys(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
+                  const uint64_t* scan, int ntx, int nty, float mh, int depth_bits, int id_bits, uint64_t* keys,
+                  int32_t* vis_idx, float* uv_compact, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 0) return GSR_OK;
+    if (id_bits < 1 || id_bits != gsr_packed_id_bits(N, ntx * nty, depth_bits)) return GSR_ERR_BAD_ARG;
+    k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, depth_bits, id_bits, keys,
+                                     nullptr, vis_idx, uv_compact);
+    return (int)cudaGetLastError();
+}
+
+size_t gsr_sort_keys_temp_bytes(int P) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortKeys((void*)nullptr, b, (uint64_t*)nullptr, (uint64_t*)nullptr, P > 0 ? P : 1, 0, 64);
+    return align256(b);
+}
+
+int gsr_sort_keys(int P, int n_tiles, int depth_bits, int id_bits, const uint64_t* keys_in, uint64_t* keys_out,
+                  void* temp, size_t temp_bytes, void* stream) {
+    if (P <= 0) return GSR_OK;
+    if (depth_bits < 1 || depth_bits > 32 || id_bits < 1) return GSR_ERR_BAD_ARG;
+    size_t b = temp_bytes;
+    // the id bits are NOT sorted: the sort is stable and pairs are emitted in gaussian order
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(temp, b, keys_in, keys_out, P, id_bits,
+                                                   id_bits + sort_end_bit(n_tiles, depth_bits), (cudaStream_t)stream);
+    return (int)e;
+}
+
+int gsr_gather_records_keys(int P, int id_bits, const uint64_t* keys_sorted, const float* records, float* out,
+                            int32_t* ids_sorted, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P <= 0) return GSR_OK;
+    k_gather_records_keys<<<BGRID((int64_t)P * 3)>>>(P, keys_sorted, (((uint64_t)1) << id_bits) - 1,
+                                                     (const float4*)records, (float4*)out, ids_sorted);
     return (int)cudaGetLastError();
 }
 

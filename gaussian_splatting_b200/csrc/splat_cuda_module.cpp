@@ -480,7 +480,6 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
     auto i32 = opt.dtype(torch::kInt32);
     const int64_t Pa = std::max<int64_t>(P, 1);
     torch::Tensor keys = torch::empty({2 * Pa}, opt.dtype(torch::kInt64));
-    torch::Tensor ids = torch::empty({Pa}, i32);
     torch::Tensor ids_sorted = torch::empty({Pa}, i32);
     torch::Tensor vis_idx = torch::empty({M}, i32);
     torch::Tensor uv = torch::empty({M, 2}, opt);
@@ -488,22 +487,41 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
     torch::Tensor stream_rec = torch::empty({Pa, GSR_REC_FLOATS}, opt);
     uint64_t* keys_a = (uint64_t*)keys.data_ptr<int64_t>();
     uint64_t* keys_b = keys_a + Pa;
-    check_rc(gsr_emit_pairs(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(),
-                            visible.data_ptr<uint8_t>(), (const uint64_t*)scan.data_ptr<int64_t>(), ntx, nty,
-                            (float)mh_dist, (int)depth_bits, keys_a, (uint32_t*)ids.data_ptr<int>(),
-                            vis_idx.data_ptr<int>(),
-                            F32PTR(uv), cur_stream()),
-             "gsr_emit_pairs");
-    const size_t sb = gsr_sort_pairs_temp_bytes((int)P);
-    torch::Tensor temp = torch::empty({(int64_t)sb}, opt.dtype(torch::kUInt8));
-    check_rc(gsr_sort_pairs((int)P, n_tiles, (int)depth_bits, keys_a, (const uint32_t*)ids.data_ptr<int>(), keys_b,
-                            (uint32_t*)ids_sorted.data_ptr<int>(), temp.data_ptr(), sb, cur_stream()),
-             "gsr_sort_pairs");
-    check_rc(gsr_tile_ranges((int)P, n_tiles, (int)depth_bits, keys_b, ranges.data_ptr<int>(), cur_stream()),
-             "gsr_tile_ranges");
-    check_rc(gsr_gather_records((int)P, (const uint32_t*)ids_sorted.data_ptr<int>(), F32PTR(records),
-                                F32PTR(stream_rec), cur_stream()),
-             "gsr_gather_records");
+    const int id_bits = gsr_packed_id_bits(N, n_tiles, (int)depth_bits);
+    if (id_bits > 0) {  // (tile | depth | id) keys, keys-only radix sort
+        check_rc(gsr_emit_keys(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(), visible.data_ptr<uint8_t>(),
+                               (const uint64_t*)scan.data_ptr<int64_t>(), ntx, nty, (float)mh_dist, (int)depth_bits,
+                               id_bits, keys_a, vis_idx.data_ptr<int>(), F32PTR(uv), cur_stream()),
+                 "gsr_emit_keys");
+        const size_t sb = gsr_sort_keys_temp_bytes((int)P);
+        torch::Tensor temp = torch::empty({(int64_t)sb}, opt.dtype(torch::kUInt8));
+        check_rc(gsr_sort_keys((int)P, n_tiles, (int)depth_bits, id_bits, keys_a, keys_b, temp.data_ptr(), sb,
+                               cur_stream()),
+                 "gsr_sort_keys");
+        check_rc(gsr_tile_ranges((int)P, n_tiles, (int)depth_bits + id_bits, keys_b, ranges.data_ptr<int>(),
+                                 cur_stream()),
+                 "gsr_tile_ranges");
+        check_rc(gsr_gather_records_keys((int)P, id_bits, keys_b, F32PTR(records), F32PTR(stream_rec),
+                                         ids_sorted.data_ptr<int>(), cur_stream()),
+                 "gsr_gather_records_keys");
+    } else {
+        torch::Tensor ids = torch::empty({Pa}, i32);
+        check_rc(gsr_emit_pairs(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(),
+                                visible.data_ptr<uint8_t>(), (const uint64_t*)scan.data_ptr<int64_t>(), ntx, nty,
+                                (float)mh_dist, (int)depth_bits, keys_a, (uint32_t*)ids.data_ptr<int>(),
+                                vis_idx.data_ptr<int>(), F32PTR(uv), cur_stream()),
+                 "gsr_emit_pairs");
+        const size_t sb = gsr_sort_pairs_temp_bytes((int)P);
+        torch::Tensor temp = torch::empty({(int64_t)sb}, opt.dtype(torch::kUInt8));
+        check_rc(gsr_sort_pairs((int)P, n_tiles, (int)depth_bits, keys_a, (const uint32_t*)ids.data_ptr<int>(), keys_b,
+                                (uint32_t*)ids_sorted.data_ptr<int>(), temp.data_ptr(), sb, cur_stream()),
+                 "gsr_sort_pairs");
+        check_rc(gsr_tile_ranges((int)P, n_tiles, (int)depth_bits, keys_b, ranges.data_ptr<int>(), cur_stream()),
+                 "gsr_tile_ranges");
+        check_rc(gsr_gather_records((int)P, (const uint32_t*)ids_sorted.data_ptr<int>(), F32PTR(records),
+                                    F32PTR(stream_rec), cur_stream()),
+                 "gsr_gather_records");
+    }
     return std::make_tuple(ids_sorted.narrow(0, 0, P), ranges, stream_rec, vis_idx, uv);
 }
 

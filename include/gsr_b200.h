@@ -221,6 +221,22 @@ int gsr_tile_ranges(int P, int n_tiles, int depth_bits, const uint64_t* keys_sor
 int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, float* records_sorted,
                        void* stream);
 
+/* Keys-only variant of the four calls above: when tile bits + depth_bits + id bits fit in 64, the gaussian id
+ * rides in the low id_bits of the key — (tile | depth | id) — and ONE cub::DeviceRadixSort::SortKeys over bits
+ * [id_bits, id_bits + depth_bits + tile bits) replaces SortPairs (8 instead of 12 bytes moved per pair and pass;
+ * the id bits are not sorted: the sort is stable and pairs are emitted in gaussian order, so ties resolve as
+ * before).  gsr_packed_id_bits returns the id width to use, or 0 when it does not fit (use the pair calls).
+ * gsr_tile_ranges takes depth_bits + id_bits as its shift. */
+int gsr_packed_id_bits(int N, int n_tiles, int depth_bits);
+int gsr_emit_keys(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
+                  const uint64_t* scan, int n_tiles_x, int n_tiles_y, float mh_dist, int depth_bits, int id_bits,
+                  uint64_t* keys, int32_t* vis_idx, float* uv_compact, void* stream);
+size_t gsr_sort_keys_temp_bytes(int P);
+int gsr_sort_keys(int P, int n_tiles, int depth_bits, int id_bits, const uint64_t* keys_in, uint64_t* keys_out,
+                  void* temp, size_t temp_bytes, void* stream);
+int gsr_gather_records_keys(int P, int id_bits, const uint64_t* keys_sorted, const float* records,
+                            float* records_sorted, int32_t* ids_sorted, void* stream);
+
 /* backward of the fused per-Gaussian stage.  grad_rgb/grad_opacity/grad_uv/grad_conic are indexed by
  * ORIGINAL gaussian index (as accumulated by gsr_render_backward; an upstream gradient on the
  * returned compact uv is scattered into grad_uv by the caller through vis_idx).  Writes dense
