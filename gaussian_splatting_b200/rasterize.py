@@ -66,12 +66,13 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
-                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out")
+                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "uv_grad_token")
 
     def __init__(self, profile=None):
         self.profile = profile  # optional list: (stage name, start event, end event) per native call
         self.grad_flat = None   # set by the backward pass: flat buffer holding all parameter gradients
         self.grad_out = None    # optional caller-owned buffer (same layout) the backward writes them into
+        self.uv_grad_token = None
 
 
 class _stage:
@@ -142,9 +143,12 @@ class _ProjectGaussians(torch.autograd.Function):
         if grad_carrier is None:
             grad_carrier = torch.zeros(9 * N, dtype=xyz.dtype, device=xyz.device)
         slab = grad_carrier.contiguous()
-        if grad_uv is not None and st.M > 0:
+        untouched = (st.uv_grad_token is not None and grad_uv is not None and slab.data_ptr() == st.uv_grad_token[2]
+                     and (grad_uv.data_ptr(), grad_uv._version) == st.uv_grad_token[:2])
+        if grad_uv is not None and st.M > 0 and not untouched:
             # total gradient on the compact uv (render contribution + anything upstream) replaces the
-            # uv section of the slab
+            # uv section of the slab.  Skipped when the incoming gradient is exactly the tensor the render
+            # backward gathered from this slab (nothing was added upstream): the slab already holds it.
             slab[4 * N:6 * N].view(N, 2).index_copy_(0, st.vis_idx, grad_uv.contiguous())
         with _stage(st, "preprocess_bwd"):
             grads = native().fused_preprocess_backward(slab, xyz, quaternion, scale, opacity_flat, sh,
@@ -173,6 +177,7 @@ class _CompositeTiles(torch.autograd.Function):
                                                   st.ranges, st.background, st.n_per_pixel, st.w_per_pixel)
         N = st.N
         grad_uv = slab[4 * N:6 * N].view(N, 2).index_select(0, st.vis_idx)
+        st.uv_grad_token = (grad_uv.data_ptr(), grad_uv._version, slab.data_ptr())
         return grad_uv, slab, None, None
 
 

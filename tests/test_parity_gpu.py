@@ -382,6 +382,23 @@ def test_against_cpu_oracle(nG, res, sig, shd):
 # ------------------------------------------------------------------------------------------------
 # edge cases
 # ------------------------------------------------------------------------------------------------
+def test_upstream_gradient_on_uv():
+    """A loss that also depends on the returned uv: the fused backward must add the upstream uv gradient to the
+    render's own (and must not when nothing is added — same result as the operator-by-operator chain)."""
+    sc = scenes.np_scene(4000, "tiny", sh_degree=0, seed=5, sigma_px=(2.0, 0.5, 0.5, 8.0))
+    G = to_t(synth.make_upstream_grad("tiny").numpy())
+    cam = Camera(sc["W"], sc["H"], to_t(sc["K"]))
+    bg = torch.full((3,), 0.5, device=dev())
+    grads = {}
+    for name, fn in (("fused", rasterize), ("unfused", rasterize_unfused)):
+        g = gaussians_from(sc)
+        image, _, uv = fn(g, to_t(sc["T"]), cam, 0.3, 500.0, 100, 3.0, True, bg)
+        ((image * G).sum() + 1e-6 * (uv * uv).sum()).backward()
+        grads[name] = (g.xyz.grad.clone(), g.scale.grad.clone())
+    for a, b in zip(grads["fused"], grads["unfused"]):
+        assert rel(a, b) < REL_TOL, rel(a, b)
+
+
 def test_everything_culled_gives_background():
     sc = scenes.np_scene(64, "tiny", sh_degree=0, seed=0)
     sc["xyz"] = sc["xyz"].copy()
