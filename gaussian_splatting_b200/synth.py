@@ -14,6 +14,7 @@ from .structs import Camera, Gaussians
 SH0 = 0.28209479177387814
 
 RESOLUTIONS = {
+    "4k": (2160, 3840, 2400.0),
     "1080p": (1080, 1920, 1200.0),
     "720p": (720, 1280, 800.0),
     "small": (192, 320, 200.0),
