@@ -120,11 +120,45 @@ static int adam_grid(long long n4) {
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+// Per-step densification statistics (splat_py/trainer.py:376-385), one pass instead of two boolean-mask
+// scatters (each with a nonzero() host sync) and four elementwise kernels:
+//   uv_grad_accum[i]  += |uv_grad[r] * (fx, fy)|   for the r-th visible gaussian i = vis_idx[r]
+//   grad_accum_count[i] += 1                        for the same i
+//   xyz_grad_accum[i] += |xyz_grad[i]|              for every gaussian
+// The scaling by the focal lengths is applied to uv_grad IN PLACE, as the reference does (:379-381).
+__global__ void __launch_bounds__(256)
+    k_densify_accumulate(int N, int M, const int32_t* __restrict__ vis_idx, float* __restrict__ uv_grad,
+                         const float* __restrict__ xyz_grad, const float* __restrict__ K,
+                         float* __restrict__ uv_acc, float* __restrict__ xyz_acc, int32_t* __restrict__ count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < M) {
+        const float fx = K[0], fy = K[4];
+        const int i = vis_idx[t];
+        const float gu = __fmul_rn(uv_grad[2 * t], fx), gv = __fmul_rn(uv_grad[2 * t + 1], fy);
+        uv_grad[2 * t] = gu;
+        uv_grad[2 * t + 1] = gv;
+        uv_acc[2 * i] = __fadd_rn(uv_acc[2 * i], fabsf(gu));
+        uv_acc[2 * i + 1] = __fadd_rn(uv_acc[2 * i + 1], fabsf(gv));
+        count[i] += 1;
+    }
+    for (int e = t; e < 3 * N; e += gridDim.x * blockDim.x) xyz_acc[e] = __fadd_rn(xyz_acc[e], fabsf(xyz_grad[e]));
+}
+
 }  // namespace gsr
 
 using namespace gsr;
 
 extern "C" {
+
+int gsr_densify_accumulate(int N, int M, const int32_t* vis_idx, float* uv_grad, const float* xyz_grad, const float* K,
+                           float* uv_grad_accum, float* xyz_grad_accum, int32_t* grad_accum_count, void* stream) {
+    if (N < 0 || M < 0 || M > N) return GSR_ERR_BAD_ARG;
+    if (N == 0) return 0;
+    const int blocks = (int)(((long long)3 * N + 255) / 256);
+    k_densify_accumulate<<<blocks, 256, 0, (cudaStream_t)stream>>>(N, M, vis_idx, uv_grad, xyz_grad, K, uv_grad_accum,
+                                                                   xyz_grad_accum, grad_accum_count);
+    return (int)cudaGetLastError();
+}
 
 int gsr_adam_step(int64_t n, float* p, const float* g, float* m, float* v, int n_sections,
                   const int64_t* section_end, const double* section_lr, double beta1, double beta2, double eps, int step,

@@ -672,6 +672,25 @@ void adam_step_sharded(int64_t lo, int64_t hi, std::vector<int64_t> peer_grad_pt
              "gsr_adam_step_sharded");
 }
 
+void densify_accumulate(torch::Tensor vis_idx, torch::Tensor uv_grad, torch::Tensor xyz_grad, torch::Tensor K,
+                        torch::Tensor uv_grad_accum, torch::Tensor xyz_grad_accum, torch::Tensor grad_accum_count) {
+    CHECK_VALID_INPUT(vis_idx); CHECK_VALID_INPUT(uv_grad); CHECK_VALID_INPUT(xyz_grad); CHECK_VALID_INPUT(K);
+    CHECK_VALID_INPUT(uv_grad_accum); CHECK_VALID_INPUT(xyz_grad_accum); CHECK_VALID_INPUT(grad_accum_count);
+    CHECK_FLOAT_TENSOR(uv_grad); CHECK_FLOAT_TENSOR(xyz_grad); CHECK_FLOAT_TENSOR(K);
+    CHECK_FLOAT_TENSOR(uv_grad_accum); CHECK_FLOAT_TENSOR(xyz_grad_accum);
+    TORCH_CHECK(vis_idx.scalar_type() == torch::kInt32 && grad_accum_count.scalar_type() == torch::kInt32,
+                "vis_idx and grad_accum_count must be int32");
+    const int64_t N = xyz_grad.size(0), M = vis_idx.numel();
+    TORCH_CHECK(uv_grad.numel() == 2 * M && uv_grad_accum.numel() == 2 * N && xyz_grad_accum.numel() == 3 * N &&
+                    grad_accum_count.numel() == N && K.numel() == 9,
+                "shape mismatch");
+    c10::cuda::CUDAGuard guard(xyz_grad.device());
+    check_rc(gsr_densify_accumulate((int)N, (int)M, vis_idx.data_ptr<int>(), F32PTR(uv_grad), F32PTR(xyz_grad), F32PTR(K),
+                                    F32PTR(uv_grad_accum), F32PTR(xyz_grad_accum), grad_accum_count.data_ptr<int>(),
+                                    cur_stream()),
+             "gsr_densify_accumulate");
+}
+
 std::string version() { return gsr_version(); }
 
 }  // namespace
@@ -706,5 +725,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("flat_section_ends", &flat_section_ends, "section ends of the flat parameter/gradient layout");
     m.def("adam_step_flat", &adam_step_flat, "Adam on the flat parameter buffer");
     m.def("adam_step_sharded", &adam_step_sharded, "reduce-scatter + Adam + all-gather over peer memory");
+    m.def("densify_accumulate", &densify_accumulate, "per-step densification statistics");
     m.def("version", &version, "library version string");
 }

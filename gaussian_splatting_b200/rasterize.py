@@ -66,7 +66,7 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
-                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "uv_grad_token")
+                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "uv_grad_token", "vis_idx32")
 
     def __init__(self, profile=None):
         self.profile = profile  # optional list: (stage name, start event, end event) per native call
@@ -128,6 +128,7 @@ class _ProjectGaussians(torch.autograd.Function):
                                                                         depth_bits)
         state.N, state.M, state.P, state.H, state.W = xyz.shape[0], M, P, H, W
         state.visible, state.vis_idx = visible, vis_idx.long()  # int64: index_copy_ needs it
+        state.vis_idx32 = vis_idx                                # int32 original, for the native ops
         state.ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec
         carrier = torch.empty(9 * xyz.shape[0], dtype=xyz.dtype, device=xyz.device)
         ctx.state = state

@@ -270,6 +270,14 @@ int gsr_adam_step_sharded(int64_t lo, int64_t hi, int world, const float* const*
                           const int64_t* section_end, const double* section_lr, double beta1, double beta2, double eps,
                           int step, void* stream);
 
+/* Per-step densification statistics of the reference's trainer (splat_py/trainer.py:376-385), in one pass:
+ * uv_grad [M,2] (the gradient of the compact uv rasterize returned, indexed like vis_idx) is scaled IN PLACE by
+ * (K[0][0], K[1][1]) and its absolute value added to uv_grad_accum [N,2] at the visible gaussians' rows;
+ * grad_accum_count [N] += 1 there; xyz_grad_accum [N,3] += |xyz_grad|.  vis_idx int32 [M] = indices of the
+ * gaussians that passed the frustum cull, ascending (gsr_emit_pairs / gsr_emit_keys produce it). */
+int gsr_densify_accumulate(int N, int M, const int32_t* vis_idx, float* uv_grad, const float* xyz_grad, const float* K,
+                           float* uv_grad_accum, float* xyz_grad_accum, int32_t* grad_accum_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

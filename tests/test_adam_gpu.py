@@ -96,3 +96,35 @@ def test_training_steps_match_torch_optimizer():
         lr = lrs[names.index(f)]
         frac = float(((a - b).abs() > 1e-6 + 1e-5 * b.abs()).float().mean())
         assert float((a - b).abs().max()) <= 2 * 5 * lr + 1e-6 and frac < 0.01, (f, float((a - b).abs().max()), frac)
+
+
+def test_densification_statistics_match_reference_ops():
+    """gsr_densify_accumulate vs the reference's update (splat_py/trainer.py:376-385) written with torch ops."""
+    from gaussian_splatting_b200.densify import DensificationStats
+
+    res, n = "small", 20000
+    cam = synth.make_camera(res, device=dev())
+    bg = torch.full((3,), 0.5, device=dev())
+    G = synth.make_upstream_grad(res, device=dev())
+    g = synth.make_gaussians(n, res, sh_degree=1, seed=2, device=dev(), requires_grad=True)
+    stats = DensificationStats(n, dev())
+    ref_uv, ref_xyz = torch.zeros(n, 2, device=dev()), torch.zeros(n, 3, device=dev())
+    ref_cnt = torch.zeros(n, dtype=torch.int32, device=dev())
+    for it in range(3):
+        T = synth.make_pose(it, 3, device=dev())
+        for f in ("xyz", "rgb", "opacity", "scale", "quaternion", "sh"):
+            getattr(g, f).grad = None
+        image, mask, uv, st = rasterize(g, T, cam, 0.3, 500.0, 100, 3.0, True, bg, return_state=True)
+        uv.retain_grad()
+        image.backward(G)
+        # reference update, on a copy of uv.grad (both scale it in place)
+        uv_grad = uv.grad.detach().clone()
+        uv_grad[:, 0] = uv_grad[:, 0] * cam.K[0, 0]
+        uv_grad[:, 1] = uv_grad[:, 1] * cam.K[1, 1]
+        ref_uv[~mask] += torch.abs(uv_grad)
+        ref_xyz += torch.abs(g.xyz.grad.detach())
+        ref_cnt += (~mask).int()
+        stats.accumulate(st, uv, g.xyz, cam.K)
+        assert torch.equal(uv.grad, uv_grad)  # scaled in place, like the reference
+    assert torch.equal(stats.uv_grad_accum, ref_uv) and torch.equal(stats.xyz_grad_accum, ref_xyz)
+    assert torch.equal(stats.grad_accum_count, ref_cnt)
