@@ -77,3 +77,20 @@ def test_synth_is_deterministic_and_shaped():
     assert torch.allclose(T0[:3, :3], T2[:3, :3].T, atol=1e-6)  # +-3 degree yaw
     G = synth.make_upstream_grad("tiny")
     assert G.shape == (64, 64, 3) and abs(G.std().item() * 3 * 64 * 64 - 1) < 0.05
+
+
+def test_flat_parameter_layout_sections():
+    """flat_adam.section_ends (host code of the native module): [xyz|quaternion|scale|opacity|rgb|sh], every
+    section starting on a 16-byte boundary, the layout gsr_preprocess_backward writes its gradients in."""
+    from gaussian_splatting_b200.flat_adam import FIELDS, section_ends
+
+    assert FIELDS == ("xyz", "quaternion", "scale", "opacity", "rgb", "sh")
+    for n, k in ((1, 0), (5, 3), (1001, 15), (3_000_000, 15)):
+        ends = section_ends(n, k)
+        widths = [3, 4, 3, 1, 3] + ([3 * k] if k else [])
+        assert len(ends) == len(widths)
+        start = 0
+        for w, e in zip(widths, ends):
+            assert start % 4 == 0 and e % 4 == 0 and 0 <= e - start - n * w < 4  # padded up to 4 floats
+            start = e
+    assert section_ends(3_000_000, 15)[-1] == 3_000_000 * 59  # no padding when N is a multiple of 4
