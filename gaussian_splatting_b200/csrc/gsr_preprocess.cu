@@ -72,6 +72,22 @@ __device__ __forceinline__ void load_view(const float* __restrict__ T, const flo
     }
 }
 
+// Whole CTA: threads 0..27 fetch one constant each (one memory latency instead of 28 dependent-issue loads by a
+// single thread); ends with a CTA barrier.  The camera centre is taken from `cam` when the caller supplies it,
+// else derived from T by thread 0.
+__device__ __forceinline__ void load_view_cta(const float* __restrict__ T, const float* __restrict__ K,
+                                              const float* __restrict__ cam, ViewConsts& vc, bool need_centre) {
+    const int t = threadIdx.x;
+    if (t < 16) vc.T[t] = T[t];
+    else if (t < 25) vc.K[t - 16] = K[t - 16];
+    else if (t < 28 && cam != nullptr) vc.cam[t - 25] = cam[t - 25];
+    __syncthreads();
+    if (need_centre && cam == nullptr) {
+        if (t == 0) camera_centre(vc.T, vc.cam);
+        __syncthreads();
+    }
+}
+
 // SH -> RGB exactly as src/precompute_sh.cu:29-56 evaluates it on cat(rgb_dc, sh_rest)
 template <int N_SH>
 __device__ __forceinline__ void sh_rgb_fused(const float* __restrict__ dc, const float* __restrict__ rest,
@@ -100,7 +116,7 @@ __device__ __forceinline__ void coop_copy(float* __restrict__ dst, const float* 
 }
 
 template <int N_SH, bool HAS_SH>
-__global__ void __launch_bounds__(PRE_THREADS)
+__global__ void __launch_bounds__(PRE_THREADS, 7)
     k_preprocess_fwd(int N, const float* __restrict__ xyz, const float* __restrict__ xyz_cam, int cam_first,
                      const float* __restrict__ quat,
                      const float* __restrict__ scale, const float* __restrict__ opa_logit,
@@ -119,24 +135,31 @@ __global__ void __launch_bounds__(PRE_THREADS)
     const int i0 = blockIdx.x * PRE_THREADS;
     const int cnt = min(PRE_THREADS, N - i0);
     const bool tma = use_tma && cnt == PRE_THREADS;
-    if (tid == 0) {
-        load_view(Tdev, Kdev, camdev, vc, HAS_SH);
-        if (HAS_SH && tma) {
-            mbar_init(&s_bar, 1);
-            fence_mbar_init();
-            const uint32_t bytes = (uint32_t)(PRE_THREADS * NR3 * sizeof(float));
-            mbar_arrive_expect_tx(&s_bar, bytes);
-            tma_load_1d(s_sh, sh_rest + (size_t)i0 * NR3, bytes, &s_bar);
-        }
+    // Latencies overlap instead of queueing up: the SH slice's bulk copy is issued first, every thread then
+    // fetches its own gaussian's parameters, and only then the view constants are fetched (cooperatively).
+    if (tid == 0 && HAS_SH && tma) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        const uint32_t bytes = (uint32_t)(PRE_THREADS * NR3 * sizeof(float));
+        mbar_arrive_expect_tx(&s_bar, bytes);
+        tma_load_1d(s_sh, sh_rest + (size_t)i0 * NR3, bytes, &s_bar);
     }
     if (HAS_SH && !tma) coop_copy(s_sh, sh_rest + (size_t)i0 * NR3, cnt * NR3);
-    __syncthreads();
     const int i = i0 + tid;
+    float x = 0.f, y = 0.f, z = 0.f, q0 = 1.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, sc0 = 0.f, sc1 = 0.f, sc2 = 0.f,
+          opl = 0.f, dc0 = 0.f, dc1 = 0.f, dc2 = 0.f;
+    if (i < N) {
+        x = xyz[i * 3 + 0]; y = xyz[i * 3 + 1]; z = xyz[i * 3 + 2];
+        q0 = quat[i * 4 + 0]; q1 = quat[i * 4 + 1]; q2 = quat[i * 4 + 2]; q3 = quat[i * 4 + 3];
+        sc0 = scale[i * 3 + 0]; sc1 = scale[i * 3 + 1]; sc2 = scale[i * 3 + 2];
+        opl = opa_logit[i];
+        dc0 = rgb_dc[i * 3 + 0]; dc1 = rgb_dc[i * 3 + 1]; dc2 = rgb_dc[i * 3 + 2];
+    }
+    load_view_cta(Tdev, Kdev, camdev, vc, HAS_SH);
     float rec[REC];
 #pragma unroll
     for (int k = 0; k < REC; ++k) rec[k] = 0.0f;
     if (i < N) {
-        const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
         float px, py, pz, u, v;
         if (xyz_cam != nullptr && i >= cam_first) {
             const float* pc = xyz_cam + (size_t)(i - cam_first) * 3;
@@ -158,8 +181,7 @@ __global__ void __launch_bounds__(PRE_THREADS)
         uint64_t pk = 0ull;
         if (vis) {
             float S6[6], S9[9], J[6], W[9], conic[3];
-            sigma_world<float>(quat[i * 4 + 0], quat[i * 4 + 1], quat[i * 4 + 2], quat[i * 4 + 3],
-                               scale[i * 3 + 0], scale[i * 3 + 1], scale[i * 3 + 2], S6);
+            sigma_world<float>(q0, q1, q2, q3, sc0, sc1, sc2, S6);
             sym6_to_full(S6, S9);
             proj_jacobian<float>(px, py, pz, vc.K[0], vc.K[4], J);
             W[0] = vc.T[0]; W[1] = vc.T[1]; W[2] = vc.T[2];
@@ -167,8 +189,8 @@ __global__ void __launch_bounds__(PRE_THREADS)
             W[6] = vc.T[8]; W[7] = vc.T[9]; W[8] = vc.T[10];
             conic_from<float>(S9, J, W, conic, nullptr);
 
-            const float opa = sigmoid_torch(opa_logit[i]);
-            float dc[3] = {rgb_dc[i * 3 + 0], rgb_dc[i * 3 + 1], rgb_dc[i * 3 + 2]};
+            const float opa = sigmoid_torch(opl);
+            float dc[3] = {dc0, dc1, dc2};
             float col[3];
             if (HAS_SH) {
                 if (tma) mbar_wait(&s_bar, 0);
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(PRE_THREADS)
 // Fused VJP.  g_rgb/g_opa/g_uv/g_conic are the per-Gaussian sums produced by the render backward
 // (indexed by original gaussian).  Order of the chain: SURVEY.md Appendix A "Per-Gaussian backward".
 template <int N_SH, bool HAS_SH>
-__global__ void __launch_bounds__(PRE_THREADS)
+__global__ void __launch_bounds__(PRE_THREADS, 6)
     k_preprocess_bwd(int N, const float* __restrict__ xyz, const float* __restrict__ quat,
                      const float* __restrict__ scale, const float* __restrict__ opa_logit,
                      const float* __restrict__ Tdev, const float* __restrict__ Kdev,
@@ -242,20 +264,30 @@ __global__ void __launch_bounds__(PRE_THREADS)
     const int i0 = blockIdx.x * PRE_THREADS;
     const int cnt = min(PRE_THREADS, N - i0);
     const bool tma = use_tma && cnt == PRE_THREADS;
-    if (tid == 0) load_view(Tdev, Kdev, camdev, vc, HAS_SH);
-    __syncthreads();
     const int i = i0 + tid;
     float gx[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, go = 0.f,
           gdc[3] = {0.f, 0.f, 0.f};
     float* my_sh = s_sh + tid * NR3;
     bool vis = false;
     if (i < N) vis = visible[i] != 0;
+    // every thread fetches its gaussian's inputs before the view constants are fetched (cooperatively): the
+    // memory latencies overlap instead of queueing up behind one thread's 28 loads
+    float x = 0.f, y = 0.f, z = 0.f, qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, opl = 0.f,
+          gcv[3] = {0.f, 0.f, 0.f}, guv[2] = {0.f, 0.f}, gov = 0.f, grv[3] = {0.f, 0.f, 0.f};
     if (vis) {
-        const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
+        x = xyz[i * 3 + 0]; y = xyz[i * 3 + 1]; z = xyz[i * 3 + 2];
+        qw = quat[i * 4 + 0]; qx = quat[i * 4 + 1]; qy = quat[i * 4 + 2]; qz = quat[i * 4 + 3];
+        s0 = scale[i * 3 + 0]; s1 = scale[i * 3 + 1]; s2 = scale[i * 3 + 2];
+        opl = opa_logit[i];
+        gcv[0] = g_conic[i * 3 + 0]; gcv[1] = g_conic[i * 3 + 1]; gcv[2] = g_conic[i * 3 + 2];
+        guv[0] = g_uv[i * 2 + 0]; guv[1] = g_uv[i * 2 + 1];
+        gov = g_opa[i];
+        grv[0] = g_rgb[i * 3 + 0]; grv[1] = g_rgb[i * 3 + 1]; grv[2] = g_rgb[i * 3 + 2];
+    }
+    load_view_cta(Tdev, Kdev, camdev, vc, HAS_SH);
+    if (vis) {
         float px, py, pz;
         transform_point<float>(vc.T, x, y, z, px, py, pz);
-        const float qw = quat[i * 4 + 0], qx = quat[i * 4 + 1], qy = quat[i * 4 + 2], qz = quat[i * 4 + 3];
-        const float s0 = scale[i * 3 + 0], s1 = scale[i * 3 + 1], s2 = scale[i * 3 + 2];
         float S6[6], S9[9], J[6], W[9];
         sigma_world<float>(qw, qx, qy, qz, s0, s1, s2, S6);
         sym6_to_full(S6, S9);
@@ -264,21 +296,21 @@ __global__ void __launch_bounds__(PRE_THREADS)
         W[3] = vc.T[4]; W[4] = vc.T[5]; W[5] = vc.T[6];
         W[6] = vc.T[8]; W[7] = vc.T[9]; W[8] = vc.T[10];
 
-        const float gc[3] = {g_conic[i * 3 + 0], g_conic[i * 3 + 1], g_conic[i * 3 + 2]};
+        const float gc[3] = {gcv[0], gcv[1], gcv[2]};
         float gS[9], gJ[6];
         conic_bwd<float>(S9, J, W, gc, gS, gJ);
         sigma_world_bwd<float>(qw, qx, qy, qz, s0, s1, s2, gS, gq, gs);
         float gp_j[3], gp_uv[3] = {0.f, 0.f, 0.f};
         proj_jacobian_bwd<float>(px, py, pz, vc.K[0], vc.K[4], gJ, gp_j);
-        project_uv_bwd<float>(px, py, pz, vc.K[0], vc.K[4], g_uv[i * 2 + 0], g_uv[i * 2 + 1], gp_uv);
+        project_uv_bwd<float>(px, py, pz, vc.K[0], vc.K[4], guv[0], guv[1], gp_uv);
         const float gp[3] = {gp_j[0] + gp_uv[0], gp_j[1] + gp_uv[1], gp_j[2] + gp_uv[2]};
         // xyz_cam = W xyz + t  =>  grad_xyz = W^T grad_xyz_cam
 #pragma unroll
         for (int k = 0; k < 3; ++k) gx[k] = W[0 + k] * gp[0] + W[3 + k] * gp[1] + W[6 + k] * gp[2];
-        const float sg = sigmoid_torch(opa_logit[i]);
-        go = g_opa[i] * ((1.0f - sg) * sg);  // torch sigmoid_backward: grad * (1 - y) * y
+        const float sg = sigmoid_torch(opl);
+        go = gov * ((1.0f - sg) * sg);  // torch sigmoid_backward: grad * (1 - y) * y
 
-        const float gr[3] = {g_rgb[i * 3 + 0], g_rgb[i * 3 + 1], g_rgb[i * 3 + 2]};
+        const float gr[3] = {grv[0], grv[1], grv[2]};
         if (HAS_SH) {
             // src/precompute_sh.cu:96-109, split into the DC column and the rest
             float dx, dy, dz, Y[N_SH];
