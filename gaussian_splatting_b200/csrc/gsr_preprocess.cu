@@ -60,18 +60,6 @@ __device__ void camera_centre(const float* __restrict__ T, float* __restrict__ c
     cam[2] = (float)A[2][4];
 }
 
-__device__ __forceinline__ void load_view(const float* __restrict__ T, const float* __restrict__ K,
-                                          const float* __restrict__ cam, ViewConsts& vc, bool need_centre = true) {
-    // called by one thread per block, result lives in shared memory
-    for (int k = 0; k < 16; ++k) vc.T[k] = T[k];
-    for (int k = 0; k < 9; ++k) vc.K[k] = K[k];
-    if (cam != nullptr) {
-        vc.cam[0] = cam[0]; vc.cam[1] = cam[1]; vc.cam[2] = cam[2];
-    } else if (need_centre) {
-        camera_centre(vc.T, vc.cam);
-    }
-}
-
 // Whole CTA: threads 0..27 fetch one constant each (one memory latency instead of 28 dependent-issue loads by a
 // single thread); ends with a CTA barrier.  The camera centre is taken from `cam` when the caller supplies it,
 // else derived from T by thread 0.
