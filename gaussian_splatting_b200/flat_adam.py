@@ -50,7 +50,9 @@ def flatten_gaussians(gaussians, flat: Optional[torch.Tensor] = None):
         old = getattr(gaussians, name)
         view = flat[start:start + old.numel()].view(old.shape)
         view.copy_(old.detach())
-        setattr(gaussians, name, view.requires_grad_(True))
+        # the reference's trainer holds nn.Parameters on an nn.Module (colmap_splat.py:58-63): keep the kind
+        new = torch.nn.Parameter(view) if isinstance(old, torch.nn.Parameter) else view.requires_grad_(True)
+        setattr(gaussians, name, new)
         start = end
     return flat, ends, names
 

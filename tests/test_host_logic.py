@@ -94,3 +94,29 @@ def test_flat_parameter_layout_sections():
             assert start % 4 == 0 and e % 4 == 0 and 0 <= e - start - n * w < 4  # padded up to 4 floats
             start = e
     assert section_ends(3_000_000, 15)[-1] == 3_000_000 * 59  # no padding when N is a multiple of 4
+
+
+def test_flatten_gaussians_keeps_values_and_kinds():
+    """flat_adam.flatten_gaussians: fields become views of ONE buffer (plain tensors stay leaf tensors, nn.Parameters
+    stay nn.Parameters, as the reference's trainer holds them), values unchanged, sections where section_ends says."""
+    import torch
+
+    from gaussian_splatting_b200.flat_adam import flatten_gaussians
+    from gaussian_splatting_b200.structs import Gaussians
+
+    n = 7
+    g = Gaussians(torch.randn(n, 3), torch.randn(n, 3), torch.randn(n, 1), torch.randn(n, 3), torch.randn(n, 4),
+                  torch.randn(n, 3, 3))
+    g.xyz = torch.nn.Parameter(g.xyz)           # mixed kinds on purpose
+    before = {f: getattr(g, f).detach().clone() for f in ("xyz", "quaternion", "scale", "opacity", "rgb", "sh")}
+    flat, ends, names = flatten_gaussians(g)
+    assert names == ["xyz", "quaternion", "scale", "opacity", "rgb", "sh"] and flat.numel() == ends[-1]
+    assert isinstance(g.xyz, torch.nn.Parameter) and not isinstance(g.rgb, torch.nn.Parameter)
+    start = 0
+    for f, e in zip(names, ends):
+        t = getattr(g, f)
+        assert t.requires_grad and t.is_leaf and torch.equal(t.detach(), before[f])
+        assert t.data_ptr() == flat.data_ptr() + 4 * start       # a view at the section's start
+        start = e
+    flat.add_(1.0)                                               # an update of the flat buffer is seen by the fields
+    assert torch.equal(g.scale.detach(), before["scale"] + 1.0)
