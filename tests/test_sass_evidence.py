@@ -1,0 +1,52 @@
+"""The built library really contains the Blackwell instructions DESIGN.md claims (runs on the CPU box:
+cuobjdump needs no GPU).  Mnemonics per /opt/skills/guides/B200_PROFILING.md: UBLKCP = 1-D TMA bulk copy
+(cp.async.bulk), SYNCS = mbarrier transaction arrive/wait, FFMA2 / FMUL2 / FADD2 = packed fp32 pairs."""
+import collections
+import re
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+LIB = Path(__file__).resolve().parents[1] / "gaussian_splatting_b200" / "libgsr_b200.so"
+
+
+def sass_counts():
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(exe).exists() or not LIB.exists():
+        pytest.skip("cuobjdump or the built library is missing")
+    text = subprocess.run([exe, "-sass", str(LIB)], check=True, capture_output=True, text=True).stdout
+    cur, counts = None, collections.defaultdict(collections.Counter)
+    for line in text.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            counts[cur][m.group(1)] += 1
+    assert "sm_100a" in text or counts, "no SASS found"
+    return counts
+
+
+def find(counts, fragment):
+    hits = [c for name, c in counts.items() if fragment in name]
+    assert hits, f"kernel {fragment} not in the library"
+    return hits[0]
+
+
+def test_tile_kernels_use_packed_fp32_and_tma():
+    counts = sass_counts()
+    for k in ("k_render_fwd", "k_render_bwd"):
+        c = find(counts, f"gsr{len(k)}{k}E")  # itanium mangling: N3gsr<len><name>E
+        assert c["FFMA2"] >= 10 and c["FMUL2"] >= 10, (k, dict(c))      # two pixels per lane, packed arithmetic
+        assert c["UBLKCP"] >= 1 and c["SYNCS"] >= 1, (k, dict(c))        # record batches arrive by TMA + mbarrier
+        assert c["BAR"] <= 4, (k, dict(c))                               # no CTA barrier in the batch loops (setup only)
+
+
+def test_per_gaussian_kernels_stage_through_tma():
+    counts = sass_counts()
+    fwd = find(counts, "k_preprocess_fwdILi16ELb1")
+    bwd = find(counts, "k_preprocess_bwdILi16ELb1")
+    assert fwd["UBLKCP"] >= 2 and bwd["UBLKCP"] >= 6   # SH slice in + records out; six gradient slices out
