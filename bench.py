@@ -275,8 +275,8 @@ def run_b200(args, rank, world, local):
                         peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                         algorithmic_bytes=alg_bytes, duration_ms=dur_ms,
                         note="76 B per (gaussian,tile) pair the kernel has to visit + 20 B per pixel; the kernel is "
-                             "instruction-issue bound (ncu: issue slots 80% busy, DRAM 4% of peak; "
-                             "profiles/r01_ncu_full_render_kernels_v3.json), so frac is small by construction",
+                             "instruction-issue bound (ncu: issue slots 77% busy, FMA / ALU pipes ~50%, DRAM 5% of peak; "
+                             "profiles/r01_ncu_full_render_kernels_v7.json), so frac is small by construction",
                         issue_roofline=issue, other_kernels=other)
 
     cpu = cpu_baseline_leg(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
