@@ -5,8 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one view: rasterize() forward + backward of the image
-against a fixed upstream gradient.  Views shard across ranks (rank r renders view step*N + r of a ring
-of poses; Gaussians are replicated; no collective on the raster path) -> weak scaling.  Rank 0 prints
+against a fixed upstream gradient.  Views shard across ranks (at step i rank r renders view (i + r) mod 8 of a
+ring of 8 poses; Gaussians are replicated; no collective on the raster path) -> weak scaling.  Rank 0 prints
 ONE JSON line (contract: see the round prompt / DESIGN.md "Measurement").
 
   value     views/s, all inputs resident in HBM, CUDA-event timed, max over ranks
@@ -44,6 +44,48 @@ SH_DEGREE = 3
 N_POSES = 8
 MY_KERNELS = ["k_preprocess_fwd", "k_emit_pairs_fused", "k_tile_ranges", "k_gather_records", "k_render_fwd",
               "k_render_bwd", "k_preprocess_bwd"]
+
+
+def log(msg):
+    """Stage progress on stderr (a lost box then shows where the arm was)."""
+    sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
+    sys.stderr.flush()
+
+
+CPU_LEG_TIMEOUT_S = 90      # hard wall-clock bound of the CPU-baseline child process
+CPU_LEG_MAX_THREADS = 32    # host threads the CPU legs may use (stated in cpu_baseline.cores)
+TORCH_CPU_SAMPLE = 300_000  # gaussians of the torch-CPU projection/SH leg (1/10 of the workload, scaled x10)
+
+
+def cpu_threads():
+    return max(1, min(CPU_LEG_MAX_THREADS, os.cpu_count() or 1))
+
+
+def cpu_baseline_sandboxed(args):
+    """Run the CPU-baseline leg in a CHILD process: bounded threads, hard timeout, never fatal.  The child
+    prints one JSON object; any failure becomes {"error": ...} in the bench line instead of a dead arm."""
+    nthreads = cpu_threads()
+    env = dict(os.environ, OMP_NUM_THREADS=str(nthreads), MKL_NUM_THREADS=str(nthreads),
+               OPENBLAS_NUM_THREADS=str(nthreads), CUDA_VISIBLE_DEVICES="", OMP_WAIT_POLICY="PASSIVE")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    cmd = [sys.executable, str(Path(__file__).resolve()), "--impl", "cpu-baseline-child"]
+    t0 = time.time()
+    try:
+        proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=CPU_LEG_TIMEOUT_S)
+    except subprocess.TimeoutExpired:
+        return {"error": f"cpu-baseline child exceeded {CPU_LEG_TIMEOUT_S}s", "cores": nthreads, "kind": "port"}
+    except Exception as e:
+        return {"error": repr(e), "cores": nthreads, "kind": "port"}
+    if proc.returncode != 0:
+        return {"error": f"cpu-baseline child rc={proc.returncode}: {proc.stderr[-300:]}", "cores": nthreads,
+                "kind": "port"}
+    try:
+        out = json.loads(proc.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"error": f"unparsable child output: {e!r}", "cores": nthreads, "kind": "port"}
+    out["child_wall_s"] = time.time() - t0
+    return out
 
 
 def dist_env():
@@ -141,10 +183,18 @@ def timed_steps(step_fn, steps, warmup, world, dev):
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    per_rank = [float(ms.item())]
     if world > 1:
         dist.barrier()
+        every = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(every, ms)
+        per_rank = [float(t.item()) for t in every]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    _LAST_PER_RANK_MS[:] = per_rank
     return float(ms.item())
+
+
+_LAST_PER_RANK_MS = []  # ms of the last timed_steps() call on every rank (explains max-over-ranks at N > 1)
 
 
 def run_b200(args, rank, world, local):
@@ -155,13 +205,17 @@ def run_b200(args, rank, world, local):
 
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
+    log("building the synthetic scene")
     g, cam, poses, poses_host, G, G_host, bg = build_scene(dev)
     cfg = synth.DEFAULTS
     K_host = cam.K.cpu().pin_memory()
     image_host = torch.empty(cam.height, cam.width, 3).pin_memory()
 
     def view_of(i):
-        return (i * world + rank) % N_POSES
+        # step i renders the `world` consecutive views i .. i+world-1 of the pose ring, rank r the r-th of them:
+        # every step covers `world` distinct views and every GPU cycles through all 8 poses, so no rank is
+        # pinned to the heaviest view (P differs by ~1.5% between poses) when the max over ranks is taken
+        return (i + rank) % N_POSES
 
     def step_resident(i):
         zero_grads(g)
@@ -203,11 +257,23 @@ def run_b200(args, rank, world, local):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()  # every rank samples its own GPU: the slowest GPU sets the max-over-ranks time
+    log("timing: resident")
     ms_res = timed_steps(step_resident, args.steps, args.warmup, world, dev)
+    per_rank_res = [m / args.steps for m in _LAST_PER_RANK_MS]
+    log(f"resident {ms_res / args.steps:.3f} ms/step; timing: e2e")
     ms_e2e = timed_steps(step_e2e, args.steps, args.warmup, world, dev)
-    clocks = sampler.stop() if rank == 0 else {}
+    per_rank_e2e = [m / args.steps for m in _LAST_PER_RANK_MS]
+    log(f"e2e {ms_e2e / args.steps:.3f} ms/step; per-stage profile")
+    clocks = sampler.stop()
+    per_rank_clocks = None
+    if world > 1:
+        import torch.distributed as dist
+
+        mine = torch.tensor([clocks.get("sm_mhz") or 0.0], device=dev, dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank_clocks = [float(t.item()) for t in every]
 
     # ---- per-stage profile + scene statistics (rank 0; separate from the timed regions) ----
     roofline, stages, stats = None, {}, {}
@@ -279,7 +345,11 @@ def run_b200(args, rank, world, local):
                              "profiles/r01_ncu_full_render_kernels_v7.json), so frac is small by construction",
                         issue_roofline=issue, other_kernels=other)
 
-    cpu = cpu_baseline_leg(args) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        log("cpu baseline (child process, bounded)")
+        cpu = cpu_baseline_sandboxed(args)
+        log("cpu baseline done")
 
     if rank != 0:
         return
@@ -294,11 +364,14 @@ def run_b200(args, rank, world, local):
                                "fixed upstream gradient",
                    "gaussians": N_GAUSS, "image": "1920x1080", "sh_degree": SH_DEGREE, "views_per_step": world,
                    "parallelism": f"views sharded 1 per GPU x{world}, gaussians replicated, no collective",
+                   "view_schedule": "step i, rank r -> pose (i + r) mod 8",
                    "l2": "per-step inputs (708 MB of parameters) exceed the 126 MB L2; no flush needed",
                    "scene": stats, "stage_ms": stages},
         "clocks": clocks,
         "e2e": {"value": views / (ms_e2e * 1e-3), "unit": "views/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+        "per_rank": {"ms_per_step": per_rank_res, "e2e_ms_per_step": per_rank_e2e, "sm_mhz": per_rank_clocks,
+                     "note": "value / e2e use the MAX over ranks; ranks differ by their GPU's clocks under load"},
         "gpu_launches": len(MY_KERNELS) * args.steps, "kernels": MY_KERNELS,
         "roofline": roofline, "cpu_baseline": cpu, "impl": "b200",
     }
@@ -316,6 +389,7 @@ def cpu_baseline_leg(args, rows=48):
     from oracle import cpu_oracle as orc
 
     t_all = time.time()
+    nthreads = int(os.environ.get("OMP_NUM_THREADS", cpu_threads()))
     g = synth.make_gaussians(N_GAUSS, RES, sh_degree=SH_DEGREE, seed=0)
     cam = synth.make_camera(RES)
     T = synth.make_pose(0, N_POSES)
@@ -342,28 +416,33 @@ def cpu_baseline_leg(args, rows=48):
     t_bwd = time.time() - t0
     scale = H / rows
     est = t_proj * 2.0 + t_bin + (t_fwd + t_bwd) * scale  # per-gaussian backward ~ per-gaussian forward
+    del g, pg
     try:
-        torch_cpu = torch_cpu_projection_sh_leg()
+        torch_cpu = torch_cpu_projection_sh_leg(n=TORCH_CPU_SAMPLE, threads=nthreads)
     except Exception as e:  # never let the auxiliary baseline take the bench down
         torch_cpu = {"error": repr(e)}
-    return {"value": 1.0 / est, "torch_cpu_projection_sh": torch_cpu, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"CPU oracle (oracle/gsr_oracle.c, OpenMP x{os.cpu_count()}): per-gaussian stage + tile binning "
-                      f"for all {N_GAUSS} gaussians, tile renderer fwd+bwd on a {rows}-row band scaled x{scale:.1f}",
+    return {"value": 1.0 / est, "torch_cpu_projection_sh": torch_cpu, "unit": "views/s", "cores": nthreads,
+            "host_cores": os.cpu_count(), "kind": "port",
+            "sample": f"CPU oracle (oracle/gsr_oracle.c, OpenMP x{nthreads} of {os.cpu_count()} host cores): "
+                      f"per-gaussian stage + tile binning for all {N_GAUSS} gaussians, tile renderer fwd+bwd on a "
+                      f"{rows}-row band scaled x{scale:.1f}; torch-CPU projection/SH leg on {TORCH_CPU_SAMPLE} "
+                      f"gaussians (scale x{N_GAUSS // TORCH_CPU_SAMPLE} for the full workload)",
             "seconds": {"project": t_proj, "binning": t_bin, "render_fwd_band": t_fwd, "render_bwd_band": t_bwd,
                         "wall": time.time() - t_all}}
 
 
-def torch_cpu_projection_sh_leg(n=N_GAUSS, reps=1):
+def torch_cpu_projection_sh_leg(n=TORCH_CPU_SAMPLE, reps=3, threads=None):
     """The reference's PyTorch-CPU projection / SH path (north_star): splat_py.utils.transform_points_torch,
     the cull expressions of splat_py/rasterize.py:33-49 and batched PyTorch restatements of the per-gaussian
     operators the reference's analytic_diff.ipynb differentiates (pinhole projection, Sigma_world, Sigma_image,
-    SH -> RGB), forward + backward on the bench's N gaussians, all host threads, median of `reps`."""
+    SH -> RGB), forward + backward on a bounded sample of `n` of the bench's gaussians, `threads` host threads,
+    median of `reps`; `seconds_fwd_bwd_scaled` extrapolates linearly to the full N (the ops are elementwise)."""
     import torch
 
     from gaussian_splatting_b200 import synth
     from gaussian_splatting_b200.utils import quaternion_to_rotation_torch, transform_points_torch
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads or cpu_threads())
     g = synth.make_gaussians(n, RES, sh_degree=SH_DEGREE, seed=0, requires_grad=True)
     cam = synth.make_camera(RES)
     T = synth.make_pose(0, N_POSES)
@@ -403,8 +482,9 @@ def torch_cpu_projection_sh_leg(n=N_GAUSS, reps=1):
         loss.backward()
         times.append(time.time() - t0)
     times.sort()
-    return {"seconds_fwd_bwd": times[len(times) // 2], "threads": torch.get_num_threads(), "cores": os.cpu_count(),
-            "gaussians": n}
+    med = times[len(times) // 2]
+    return {"seconds_fwd_bwd": med, "seconds_fwd_bwd_scaled": med * (N_GAUSS / n), "threads": torch.get_num_threads(),
+            "cores": os.cpu_count(), "gaussians": n, "scaled_to": N_GAUSS}
 
 
 def run_reference(args, rank, world, local):
@@ -446,7 +526,10 @@ def run_reference(args, rank, world, local):
         "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": {"workload": "synthetic 3M Gaussians, 1080p, SH deg 3; same scene/poses as the b200 arm",
                    "how": "unmodified joeyan/gaussian_splatting: its CUDA extension compiled for sm_100 "
-                          "(oracle/_ref) driven by its own splat_py.rasterize.rasterize + backward, on GPU 0"},
+                          "(oracle/_ref) driven by its own splat_py.rasterize.rasterize + backward, on GPU 0",
+                   "launched_world_size": world,
+                   "note": "the reference has no multi-GPU path: under torchrun only rank 0 runs, so this is a "
+                           "1-GPU number whatever --gpus says (n_gpus is 1 in this line)"},
         "clocks": clocks,
         "cpu_baseline": {"value": value, "unit": "views/s", "cores": 0, "kind": "reference",
                          "sample": "full workload on the GPU: the reference implements this path only in CUDA "
@@ -459,7 +542,9 @@ def run_reference(args, rank, world, local):
 def run_reference_cpu(args, rank):
     if rank != 0:
         return
-    cpu = cpu_baseline_leg(args)
+    cpu = cpu_baseline_sandboxed(args)
+    if "value" not in cpu:
+        return emit({"impl": "reference", "unavailable": f"cpu port failed: {cpu.get('error')}"})
     line = {
         "metric": METRIC, "value": cpu["value"], "unit": "views/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
@@ -497,13 +582,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cpu"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cpu", "cpu-baseline-child"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank, world, local = dist_env()
+    if args.impl == "cpu-baseline-child":  # internal: the sandboxed CPU leg (see cpu_baseline_sandboxed)
+        return emit(cpu_baseline_leg(args))
     if args.impl == "reference-cpu":
         return run_reference_cpu(args, rank)
+    log(f"impl={args.impl} rank={rank}/{world} importing torch")
     import torch
 
     if not torch.cuda.is_available():
@@ -516,8 +604,8 @@ def main():
                 run_reference(args, rank, world, local)
             return
         torch.cuda.set_device(local)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
+        # NCCL_DEBUG is left as the launcher set it: file descriptor 1 already points at stderr
+        # (protect_stdout), so whatever NCCL prints cannot corrupt the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     try:
         if args.impl == "reference":

@@ -574,7 +574,9 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
                                                      torch::Tensor camera_T_world, torch::Tensor K,
                                                      c10::optional<torch::Tensor> camera_centre,
                                                      torch::Tensor visible,
-                                                     c10::optional<torch::Tensor> out_flat) {
+                                                     c10::optional<torch::Tensor> out_flat,
+                                                     c10::optional<torch::Tensor> grad_uv_compact,
+                                                     c10::optional<torch::Tensor> scan) {
     CHECK_VALID_INPUT(slab); CHECK_FLOAT_TENSOR(slab);
     const int64_t N = xyz.size(0);
     TORCH_CHECK(slab.numel() == N * 9, "gradient slab must hold 9 floats per gaussian");
@@ -585,6 +587,16 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
     const float* g_uv = g_opa + (size_t)N;
     const float* g_conic = g_uv + (size_t)N * 2;
     const int n_rest = sh_rest.has_value() ? (int)sh_rest->size(2) : 0;
+    const float* g_uv_compact = nullptr;
+    const uint64_t* scan_ptr = nullptr;
+    if (grad_uv_compact.has_value() && grad_uv_compact->numel() > 0) {
+        CHECK_VALID_INPUT((*grad_uv_compact)); CHECK_FLOAT_TENSOR((*grad_uv_compact));
+        TORCH_CHECK(scan.has_value() && scan->numel() == N && scan->scalar_type() == torch::kInt64,
+                    "grad_uv_compact needs the packed scan of the forward pass");
+        TORCH_CHECK(grad_uv_compact->dim() == 2 && grad_uv_compact->size(1) == 2, "grad_uv_compact must be Mx2");
+        g_uv_compact = grad_uv_compact->data_ptr<float>();
+        scan_ptr = (const uint64_t*)scan->data_ptr<int64_t>();
+    }
     // All parameter gradients of a view live in ONE allocation, [xyz 3N | quaternion 4N | scale 3N |
     // opacity N | rgb 3N | sh 3*n_rest*N], every section starting on a 16-byte boundary (TMA bulk stores):
     // a trainer that sums gradients over views / ranks reduces that one buffer (view_parallel.py).
@@ -614,7 +626,8 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
     check_rc(gsr_preprocess_backward((int)N, n_rest, F32PTR(xyz), F32PTR(quaternion), F32PTR(scale),
                                      F32PTR(opacity_logit), F32PTR(camera_T_world), F32PTR(K),
                                      camera_centre.has_value() ? camera_centre->data_ptr<float>() : nullptr,
-                                     visible.data_ptr<uint8_t>(), g_rgb, g_opa, g_uv, g_conic, F32PTR(o_xyz),
+                                     visible.data_ptr<uint8_t>(), g_rgb, g_opa, g_uv, g_conic, g_uv_compact,
+                                     scan_ptr, F32PTR(o_xyz),
                                      F32PTR(o_q), F32PTR(o_s), F32PTR(o_o), F32PTR(o_dc),
                                      n_rest ? F32PTR(g_sh) : nullptr, cur_stream()),
              "gsr_preprocess_backward");

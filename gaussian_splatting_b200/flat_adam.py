@@ -74,7 +74,15 @@ class FlatAdam:
         flat, ends, names = flatten_gaussians(gaussians)
         return cls(flat, ends, [base_lr * multipliers[n] for n in names], **kw)
 
-    def step(self, grad_flat: torch.Tensor) -> None:
+    def step(self, grad_flat) -> None:
+        """`grad_flat`: the flat gradient buffer in the native layout (`state.grad_flat`), or a
+        view_parallel.GradientBucket — which must be in the native layout (a "packed" bucket would apply the
+        gradients to the wrong sections with the wrong learning rates, so it is rejected)."""
+        if hasattr(grad_flat, "flat") and hasattr(grad_flat, "layout"):
+            if grad_flat.layout != "native":
+                raise ValueError("FlatAdam.step needs a bucket in the native flat layout "
+                                 "(GradientBucket.adopt(flat, gaussians) or GradientBucket.native_layout)")
+            grad_flat = grad_flat.flat
         assert grad_flat.numel() == self.p.numel(), "gradient buffer does not match the parameter layout"
         self.t += 1
         native().adam_step_flat(self.p, grad_flat, self.m, self.v, self.ends, self.lrs, self.betas[0], self.betas[1],

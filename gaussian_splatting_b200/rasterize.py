@@ -48,6 +48,57 @@ CUBLAS_BATCH_CHUNK = 65535   # gridDim limit cuBLAS batches against
 SMALL_BATCH = 1024           # chunks below ~300 use another kernel (measured: 100 differs, 300 matches)
 
 
+_TRANSFORM_OK = {}  # device index -> bool: did the in-kernel transform reproduce torch.matmul on this device?
+
+
+def in_kernel_transform_ok(device, n: int = 70_000, seed: int = 1234) -> bool:
+    """One-time self-check per device (a cuBLAS / torch upgrade could change the rounding order the fused
+    kernel mimics): `n` random points (more than one 65535-matrix cuBLAS chunk) under a random rigid pose, camera
+    z and uv from the in-kernel transform compared BIT FOR BIT with the reference's op
+    (splat_py/utils.py:60-72, torch.matmul).  On a mismatch the fused path forms positions with torch.matmul
+    itself from then on (the reference's own op on the GPU, +2.3 ms at 3M points) and says so once."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ok = _TRANSFORM_OK.get(idx)
+    if ok is not None:
+        return ok
+    import math
+    import warnings
+
+    ext = native()
+    gen = torch.Generator().manual_seed(seed)
+    xyz = (torch.rand(n, 3, generator=gen) * torch.tensor([8.0, 6.0, 10.0]) + torch.tensor([-4.0, -3.0, 1.0])).to(device)
+    q = torch.randn(4, generator=gen)
+    w, x, y, z = (q / q.norm()).tolist()
+    T = torch.eye(4)
+    T[:3, :3] = torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                              [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                              [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    T[:3, 3] = torch.randn(3, generator=gen)
+    T = T.to(device)
+    K = torch.tensor([[1200.0, 0.0, 960.0], [0.0, 1200.0, 540.0], [0.0, 0.0, 1.0]], device=device)
+    quat = torch.zeros(n, 4, device=device)
+    quat[:, 0] = 1.0
+    zeros3, zeros1 = torch.zeros(n, 3, device=device), torch.zeros(n, device=device)
+    big = 1e30
+    with torch.no_grad():
+        rec, zkey, _, _ = ext.fused_preprocess_forward(xyz, None, quat, zeros3, zeros1, zeros3, None, T, K, None, 1080,
+                                                       1920, -big, big, big, 3.0, 0)
+        ref = transform_points_torch(xyz, T)
+        zref = ref[:, 2].contiguous().view(torch.int32)
+        zref = torch.where(zref < 0, ~zref, zref | -2**31)
+        uv = torch.zeros(n, 2, device=device)
+        ext.camera_projection_cuda(ref, K, uv)
+        fin = torch.isfinite(uv).all(dim=1) & torch.isfinite(rec[:, :2]).all(dim=1)
+        same = bool((zkey == zref).all()) and bool((rec[:, 0:2][fin].contiguous().view(torch.int32)
+                                                    == uv[fin].contiguous().view(torch.int32)).all())
+    _TRANSFORM_OK[idx] = same
+    if not same:
+        warnings.warn("gaussian_splatting_b200: the in-kernel world->camera transform no longer reproduces "
+                      "torch.matmul bit for bit on this device (cuBLAS changed its rounding order?); "
+                      "falling back to torch.matmul for camera-frame positions", RuntimeWarning)
+    return same
+
+
 def _depth_key_params(near, far):
     """(base, bits): depth keys are float bits of z minus `base`; `bits` low bits are significant."""
     import math
@@ -56,9 +107,13 @@ def _depth_key_params(near, far):
     def fbits(v):
         return struct.unpack("<I", struct.pack("<f", v))[0]
 
-    if near > 0.0 and math.isfinite(far) and far > near:
-        b0, b1 = fbits(near), fbits(far)
-        return b0, max(1, (b1 - b0).bit_length())
+    FLT_MAX = 3.4028234663852886e38
+    if near > 0.0 and math.isfinite(far) and near < far <= FLT_MAX:
+        b0, b1 = fbits(near), fbits(far)  # struct.pack rounds to nearest: a tiny `near` can round to 0.0f
+        if b0 > 0 and b1 > b0:
+            return b0, max(1, (b1 - b0).bit_length())
+    # no usable positive range (near <= 0 or rounding to 0.0f, far infinite / beyond FLT_MAX / NaN): full 32-bit
+    # order-preserving keys (depth_key() sets bit 31, so depth_bits MUST be 32 whenever the base is 0)
     return 0, 32
 
 
@@ -66,13 +121,12 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
-                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "uv_grad_token", "vis_idx32")
+                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "vis_idx32", "scan")
 
     def __init__(self, profile=None):
         self.profile = profile  # optional list: (stage name, start event, end event) per native call
         self.grad_flat = None   # set by the backward pass: flat buffer holding all parameter gradients
         self.grad_out = None    # optional caller-owned buffer (same layout) the backward writes them into
-        self.uv_grad_token = None
 
 
 class _stage:
@@ -105,7 +159,7 @@ class _ProjectGaussians(torch.autograd.Function):
         # splat_py/utils.py:60-72), because their bits decide tile membership and the 1/255 skip and the
         # rounding order inside cuBLAS is not ours to pin; IN_KERNEL_TRANSFORM folds it into the kernel.
         N = xyz.shape[0]
-        if IN_KERNEL_TRANSFORM and N >= IN_KERNEL_TRANSFORM_MIN_N:
+        if IN_KERNEL_TRANSFORM and N >= IN_KERNEL_TRANSFORM_MIN_N and in_kernel_transform_ok(xyz.device):
             # cuBLAS runs the batched product in chunks of 65535 matrices; a short last chunk goes through
             # its small-batch kernel (different rounding order), so that tail is formed by torch itself
             tail = N % CUBLAS_BATCH_CHUNK
@@ -123,6 +177,11 @@ class _ProjectGaussians(torch.autograd.Function):
                 pad, mh, depth_base)
         total = int(scan[-1].item()) if xyz.shape[0] > 0 else 0  # the one host sync
         M, P = total >> 32, total & 0xFFFFFFFF
+        # M and P share one u64 scan (M<<32 | P) and the native entry points index pairs with int32: a scene
+        # with >= 2^31 (gaussian, tile) pairs must fail loudly, not wrap into an empty render
+        if M > N or P >= 2**31:
+            raise RuntimeError(f"rasterize: {P} (gaussian, tile) pairs / {M} visible of {N} gaussians exceed the "
+                               "int32 pair index of the native path (P must be < 2^31)")
         with _stage(state, "bin_sort_gather"):
             ids_sorted, ranges, stream_rec, vis_idx, uv = ext.fused_bin(records, zkey, visible, scan, M, P, H, W, mh,
                                                                         depth_bits)
@@ -130,6 +189,7 @@ class _ProjectGaussians(torch.autograd.Function):
         state.visible, state.vis_idx = visible, vis_idx.long()  # int64: index_copy_ needs it
         state.vis_idx32 = vis_idx                                # int32 original, for the native ops
         state.ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec
+        state.scan = scan
         carrier = torch.empty(9 * xyz.shape[0], dtype=xyz.dtype, device=xyz.device)
         ctx.state = state
         ctx.has_sh = sh is not None
@@ -144,16 +204,16 @@ class _ProjectGaussians(torch.autograd.Function):
         if grad_carrier is None:
             grad_carrier = torch.zeros(9 * N, dtype=xyz.dtype, device=xyz.device)
         slab = grad_carrier.contiguous()
-        untouched = (st.uv_grad_token is not None and grad_uv is not None and slab.data_ptr() == st.uv_grad_token[2]
-                     and (grad_uv.data_ptr(), grad_uv._version) == st.uv_grad_token[:2])
-        if grad_uv is not None and st.M > 0 and not untouched:
-            # total gradient on the compact uv (render contribution + anything upstream) replaces the
-            # uv section of the slab.  Skipped when the incoming gradient is exactly the tensor the render
-            # backward gathered from this slab (nothing was added upstream): the slab already holds it.
-            slab[4 * N:6 * N].view(N, 2).index_copy_(0, st.vis_idx, grad_uv.contiguous())
+        # The gradient autograd hands us for the compact uv is the TOTAL (render contribution + anything the
+        # caller added upstream of uv); the kernel reads it directly, row = rank among the visible gaussians
+        # (from the forward's scan), instead of the slab's uv section.  Incoming gradients are never edited.
+        guv = None
+        if grad_uv is not None and st.M > 0:
+            guv = grad_uv.contiguous()
         with _stage(st, "preprocess_bwd"):
             grads = native().fused_preprocess_backward(slab, xyz, quaternion, scale, opacity_flat, sh,
-                                                       camera_T_world, K, centre, st.visible, st.grad_out)
+                                                       camera_T_world, K, centre, st.visible, st.grad_out,
+                                                       guv, st.scan if guv is not None else None)
         g_xyz, g_q, g_s, g_o, g_dc = grads[:5]
         g_sh = grads[5] if ctx.has_sh else None
         st.grad_flat = grads[-1]  # the one allocation all parameter gradients of this view are views of
@@ -178,7 +238,6 @@ class _CompositeTiles(torch.autograd.Function):
                                                   st.ranges, st.background, st.n_per_pixel, st.w_per_pixel)
         N = st.N
         grad_uv = slab[4 * N:6 * N].view(N, 2).index_select(0, st.vis_idx)
-        st.uv_grad_token = (grad_uv.data_ptr(), grad_uv._version, slab.data_ptr())
         return grad_uv, slab, None, None
 
 

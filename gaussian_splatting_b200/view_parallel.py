@@ -17,7 +17,7 @@ Either way `all_reduce()` hands one buffer to NCCL: one launch, `async_op=True` 
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence
+from typing import Dict, Iterable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -38,6 +38,13 @@ class GradientBucket:
     changes, e.g. after densification); then per step: bucket.zero(); loss.backward(); bucket.all_reduce().
     """
 
+    # `layout` says how `flat` is arranged, because consumers of the flat buffer depend on it:
+    #   "native"  the rasterizer's / FlatAdam's layout: sections in flat_adam.FIELDS order
+    #             [xyz | quaternion | scale | opacity | rgb | sh], every section end 16-byte aligned
+    #             (native().flat_section_ends); what the fused backward writes and gsr_adam_step reads
+    #   "packed"  the caller's parameter order, no padding: good for the collective only
+    # FlatAdam.step() refuses a bucket that is not "native".
+
     def __init__(self, params: Sequence[torch.Tensor]):
         self.params: List[torch.Tensor] = [p for p in params if p is not None]
         assert self.params, "no parameters"
@@ -46,36 +53,76 @@ class GradientBucket:
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
         self.views: List[torch.Tensor] = []
+        self.layout, self.zero_copy = "packed", False
         off = 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view(p.shape))
             off += p.numel()
 
     @classmethod
-    def for_gaussians(cls, gaussians) -> "GradientBucket":
-        return cls([getattr(gaussians, f, None) for f in PARAM_FIELDS])
+    def native_layout(cls, named: Dict[str, Optional[torch.Tensor]]) -> "GradientBucket":
+        """Bucket in the rasterizer's own flat layout (see `layout` above) for the parameters given by field
+        name.  `params` / `views` are in flat_adam.FIELDS order."""
+        from .flat_adam import FIELDS, section_ends
+
+        names = [f for f in FIELDS if named.get(f) is not None]
+        assert "xyz" in names, "native layout needs at least xyz"
+        params = [named[f] for f in names]
+        n = named["xyz"].shape[0]
+        n_rest = 0 if named.get("sh") is None else named["sh"].shape[2]
+        ends = section_ends(n, n_rest)
+        assert len(ends) == len(names), "parameter set does not match the native flat layout"
+        b = cls.__new__(cls)
+        b.params = list(params)
+        dev, dt = params[0].device, params[0].dtype
+        b.numel = int(ends[-1])
+        b.flat = torch.zeros(b.numel, dtype=dt, device=dev)
+        b.views, start = [], 0
+        for p_, end in zip(params, ends):
+            assert start + p_.numel() <= end
+            b.views.append(b.flat[start:start + p_.numel()].view(p_.shape))
+            start = int(end)
+        b.layout, b.zero_copy = "native", False
+        return b
 
     @classmethod
-    def adopt(cls, flat: torch.Tensor, params: Sequence[torch.Tensor]) -> "GradientBucket":
+    def for_gaussians(cls, gaussians, native: bool = True) -> "GradientBucket":
+        named = {f: getattr(gaussians, f, None) for f in PARAM_FIELDS}
+        if native:
+            return cls.native_layout(named)
+        return cls([named[f] for f in PARAM_FIELDS])
+
+    @classmethod
+    def adopt(cls, flat: torch.Tensor, params, names: Optional[Sequence[str]] = None) -> "GradientBucket":
         """Zero-copy bucket over the buffer the fused backward already produced: `rasterize(...,
         return_state=True)` leaves all parameter gradients of the view as views of `state.grad_flat`, and
         autograd installs those views as `.grad` when the parameters had no gradient yet (`p.grad = None`
         before `backward()`).  Falls back to a flatten copy when a gradient lives elsewhere (accumulated
-        over several views, or produced by the unfused operator chain)."""
-        params = [p for p in params if p is not None]
+        over several views, or produced by the unfused operator chain).
+
+        `params` is a Gaussians-like object, a {field name: tensor} dict, or a sequence of tensors with `names`
+        giving their field names: then the fallback copy is built in the NATIVE layout, so the bucket can feed
+        FlatAdam either way.  A bare sequence without names falls back to a "packed" bucket (collective only)."""
+        named = None
+        if isinstance(params, dict):
+            named = params
+        elif hasattr(params, "xyz"):
+            named = {f: getattr(params, f, None) for f in PARAM_FIELDS}
+        elif names is not None:
+            named = dict(zip(names, params))
+        plist = [p for p in (named.values() if named is not None else params) if p is not None]
         lo = flat.data_ptr()
         hi = lo + flat.numel() * flat.element_size()
-        if all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in params):
+        if all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in plist):
             b = cls.__new__(cls)
-            b.params, b.flat, b.numel = list(params), flat, flat.numel()
-            b.views = [p.grad for p in params]
-            b.zero_copy = True
+            b.params, b.flat, b.numel = list(plist), flat, flat.numel()
+            b.views = [p.grad for p in plist]
+            b.zero_copy, b.layout = True, "native"
             return b
-        b = cls(params)
+        b = cls.native_layout(named) if named is not None else cls(plist)
         for p, v in zip(b.params, b.views):
             if p.grad is not None:
                 v.copy_(p.grad)
-        b.zero_copy = False
         return b.attach()
 
     def attach(self) -> "GradientBucket":

@@ -238,13 +238,16 @@ int gsr_gather_records_keys(int P, int id_bits, const uint64_t* keys_sorted, con
                             float* records_sorted, int32_t* ids_sorted, void* stream);
 
 /* backward of the fused per-Gaussian stage.  grad_rgb/grad_opacity/grad_uv/grad_conic are indexed by
- * ORIGINAL gaussian index (as accumulated by gsr_render_backward; an upstream gradient on the
- * returned compact uv is scattered into grad_uv by the caller through vis_idx).  Writes dense
+ * ORIGINAL gaussian index (as accumulated by gsr_render_backward).  When grad_uv_compact is not NULL it is
+ * the TOTAL gradient on the compact uv [M,2] that rasterize returned (render contribution + anything the
+ * caller added upstream, what autograd hands to the projection node) and replaces grad_uv: the row of visible
+ * gaussian i is (scan[i] >> 32) - 1, scan = the packed inclusive scan of gsr_preprocess_forward.  Writes dense
  * parameter gradients for all N gaussians (zeros for culled ones). */
 int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
                             const float* scale, const float* opacity_logit, const float* camera_T_world,
                             const float* K, const float* camera_centre, const uint8_t* visible, const float* grad_rgb,
                             const float* grad_opacity, const float* grad_uv, const float* grad_conic,
+                            const float* grad_uv_compact, const uint64_t* scan,
                             float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
                             float* g_rgb_dc, float* g_sh_rest, void* stream);
 

@@ -128,3 +128,118 @@ def test_densification_statistics_match_reference_ops():
         assert torch.equal(uv.grad, uv_grad)  # scaled in place, like the reference
     assert torch.equal(stats.uv_grad_accum, ref_uv) and torch.equal(stats.xyz_grad_accum, ref_xyz)
     assert torch.equal(stats.grad_accum_count, ref_cnt)
+
+
+def _sharded_split(n, world):
+    per = ((n // 4 + world - 1) // world) * 4
+    return [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_adam_kernel_emulated_ranks_on_one_gpu(world):
+    """gsr_adam_step_sharded (reduce-scatter + Adam + all-gather in one kernel, csrc/gsr_adam.cu) with `world`
+    EMULATED ranks on one device: every "rank" owns its own parameter and gradient buffer (the peer pointers then
+    simply point at the same device), each rank's kernel is launched in turn.  Must equal: average the gradients
+    over ranks (rank order), then FlatAdam on the average — and leave every replica bit-identical.  This is the
+    single-GPU guard of the kernel the 2-GPU test below runs over NVLink."""
+    n_g = 5001
+    ends = section_ends(n_g, 15)
+    lrs = [0.002 * REFERENCE_LR_MULTIPLIERS[f] for f in FIELDS]
+    total = ends[-1]
+    gen = torch.Generator(device=dev()).manual_seed(11)
+    p0 = torch.randn(total, device=dev(), generator=gen)
+    params = [p0.clone() for _ in range(world)]
+    grads = [torch.empty(total, device=dev()) for _ in range(world)]
+    split = _sharded_split(total, world)
+    ms = [torch.zeros(hi - lo, device=dev()) for lo, hi in split]
+    vs = [torch.zeros(hi - lo, device=dev()) for lo, hi in split]
+    ref_p = p0.clone()
+    ref = FlatAdam(ref_p, ends, lrs)
+    ext = __import__("gaussian_splatting_b200").native()
+    for step in range(1, 5):
+        for r in range(world):
+            grads[r].copy_(torch.randn(total, device=dev(), generator=gen) * 10.0 ** (-3.0 * torch.rand(total, device=dev(), generator=gen)))
+        mean = grads[0].clone()
+        for r in range(1, world):
+            mean += grads[r]          # rank order, like the kernel
+        mean *= 1.0 / world   # the kernel scales by the float reciprocal
+        ref.step(mean)
+        gp, pp = [int(t.data_ptr()) for t in grads], [int(t.data_ptr()) for t in params]
+        for r, (lo, hi) in enumerate(split):
+            ext.adam_step_sharded(lo, hi, gp, pp, r, ms[r], vs[r], ends, lrs, 0.9, 0.999, 1e-8, step)
+        torch.cuda.synchronize()
+        for r in range(1, world):
+            assert torch.equal(params[r], params[0]), f"replica {r} differs after step {step}"
+        err = float((params[0] - ref_p).abs().max())
+        assert err <= 1e-6 * float(ref_p.abs().max()), (step, err)
+    m_all, v_all = torch.cat(ms), torch.cat(vs)
+    assert float((m_all - ref.m).abs().max()) <= 1e-6 * float(ref.m.abs().max())
+    assert float((v_all - ref.v).abs().max()) <= 1e-6 * float(ref.v.abs().max())
+
+
+def _sharded_worker(rank, world, port, q):
+    import os
+
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    d = torch.device(f"cuda:{rank}")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=d)
+    try:
+        from gaussian_splatting_b200.flat_adam import ShardedFlatAdam
+
+        n_g = 20001
+        ends = section_ends(n_g, 15)
+        lrs = [0.002 * REFERENCE_LR_MULTIPLIERS[f] for f in FIELDS]
+        total = ends[-1]
+        p_sym = symm_mem.empty(total, dtype=torch.float32, device=d)
+        g_sym = symm_mem.empty(total, dtype=torch.float32, device=d)
+        gen = torch.Generator(device=d).manual_seed(5)       # same parameters on every rank
+        p_sym.copy_(torch.randn(total, device=d, generator=gen))
+        opt = ShardedFlatAdam(p_sym, g_sym, ends, lrs)
+        ref_p = p_sym.clone()
+        ref = FlatAdam(ref_p, ends, lrs)
+        worst = 0.0
+        for step in range(4):
+            grank = torch.Generator(device=d).manual_seed(100 + 10 * step + rank)  # a different "view" per rank
+            g_sym.copy_(torch.randn(total, device=d, generator=grank) * 1e-2)
+            mean = g_sym.clone()
+            dist.all_reduce(mean, op=dist.ReduceOp.SUM)  # NCCL path: all-reduce + flat Adam
+            mean /= world
+            ref.step(mean)
+            opt.step()
+            torch.cuda.synchronize()
+            worst = max(worst, float((p_sym - ref_p).abs().max()) / float(ref_p.abs().max()))
+        gathered = [torch.empty_like(p_sym) for _ in range(world)]
+        dist.all_gather(gathered, p_sym.clone())
+        same = all(torch.equal(gathered[0], t) for t in gathered)
+        if rank == 0:
+            q.put((worst, same))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NVLink peer memory)")
+def test_sharded_adam_matches_allreduce_plus_flat():
+    """ShardedFlatAdam over real symmetric memory on 2 GPUs: same parameters as NCCL all-reduce(avg) + FlatAdam
+    (summation order differs from NCCL's by at most rounding), replicas bit-identical."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    worst, same = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert same, "parameter replicas differ"
+    assert worst < 1e-6, worst

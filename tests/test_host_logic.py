@@ -120,3 +120,45 @@ def test_flatten_gaussians_keeps_values_and_kinds():
         start = e
     flat.add_(1.0)                                               # an update of the flat buffer is seen by the fields
     assert torch.equal(g.scale.detach(), before["scale"] + 1.0)
+
+
+def test_gradient_bucket_fallback_keeps_the_native_layout():
+    """the copy fallback of GradientBucket.adopt must be laid out like state.grad_flat
+    ([xyz | quaternion | scale | opacity | rgb | sh], 16-byte aligned section ends) when the field names are
+    known, and FlatAdam.step must refuse a bucket in any other layout."""
+    import pytest
+    import torch
+
+    from gaussian_splatting_b200.flat_adam import FIELDS, FlatAdam, section_ends
+    from gaussian_splatting_b200.structs import Gaussians
+    from gaussian_splatting_b200.view_parallel import GradientBucket
+
+    n, k = 6, 15  # n % 4 != 0: section ends are padded
+    torch.manual_seed(0)
+    g = Gaussians(xyz=torch.randn(n, 3), rgb=torch.randn(n, 3), opacity=torch.randn(n, 1), scale=torch.randn(n, 3),
+                  quaternion=torch.randn(n, 4), sh=torch.randn(n, 3, k))
+    for f in FIELDS:
+        getattr(g, f).requires_grad_(True)
+        getattr(g, f).grad = torch.full_like(getattr(g, f), float(FIELDS.index(f) + 1))
+    other = torch.empty(8)  # gradients live elsewhere -> copy fallback
+    b = GradientBucket.adopt(other, g)
+    assert not b.zero_copy and b.layout == "native"
+    ends = section_ends(n, k)
+    assert b.flat.numel() == ends[-1]
+    start = 0
+    for i, (f, end) in enumerate(zip(FIELDS, ends)):
+        numel = getattr(g, f).numel()
+        assert torch.all(b.flat[start:start + numel] == float(i + 1)), f
+        assert torch.all(b.flat[start + numel:end] == 0.0)  # padding
+        assert getattr(g, f).grad.data_ptr() == b.flat[start:].data_ptr()  # attached
+        start = end
+    # a bare list carries no field names: packed layout, good for the collective only
+    packed = GradientBucket.adopt(other, [g.xyz, g.rgb, g.opacity, g.scale, g.quaternion, g.sh])
+    assert packed.layout == "packed"
+
+    class _Opt(FlatAdam):
+        def __init__(self):  # no device buffers needed for the layout check
+            self.p = torch.empty(ends[-1])
+
+    with pytest.raises(ValueError):
+        _Opt().step(packed)

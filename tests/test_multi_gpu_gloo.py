@@ -1,5 +1,6 @@
-"""N>1 host logic on CPU with gloo, world_size 2: the view -> rank assignment bench.py uses covers every
-view exactly once per step, and the max-over-ranks timing reduction behaves (no data-path collective
+"""N>1 host logic on CPU with gloo, world_size 2: the view -> rank assignment bench.py uses (step i, rank r ->
+pose (i + r) mod 8) renders `world` distinct views per step and cycles every rank through all poses, and the
+max-over-ranks timing reduction behaves (no data-path collective
 exists on the raster path — views are independent)."""
 import os
 import socket
@@ -19,7 +20,7 @@ def _worker(rank, world, port, steps, n_poses, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        views = [(i * world + rank) % n_poses for i in range(steps)]
+        views = [(i + rank) % n_poses for i in range(steps)]  # bench.py run_b200.view_of
         mine = torch.zeros(steps * world, dtype=torch.int64)
         for i, v in enumerate(views):
             mine[i * world + rank] = v + 1
@@ -36,7 +37,7 @@ def _worker(rank, world, port, steps, n_poses, out):
 def test_view_sharding_two_ranks():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    world, steps, n_poses = 2, 6, 8
+    world, steps, n_poses = 2, 8, 8
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, steps, n_poses, q)) for r in range(world)]
     for p in procs:
@@ -46,7 +47,11 @@ def test_view_sharding_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(s > 0 for s in slots)                       # every (step, rank) slot rendered once
-    assert [s - 1 for s in slots] == [k % n_poses for k in range(steps * world)]  # consecutive views, no overlap
+    v = [s - 1 for s in slots]
+    for i in range(steps):                                 # per step: `world` distinct, consecutive views
+        assert v[i * world:(i + 1) * world] == [(i + r) % n_poses for r in range(world)]
+    for r in range(world):                                 # over n_poses steps every rank renders every pose once
+        assert sorted(v[r::world]) == list(range(n_poses))
     assert ms == 15.0                                      # max over ranks
 
 

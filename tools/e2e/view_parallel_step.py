@@ -119,11 +119,11 @@ def main():
             opt.step()  # barrier, reduce-scatter + Adam + all-gather in one kernel, barrier
             bucket_bytes, zero_copy = grads_sym.numel() * 4, True
         else:
-            bucket = GradientBucket.adopt(state.grad_flat, params)
+            bucket = GradientBucket.adopt(state.grad_flat, g)
             bucket.all_reduce(average=True)
             e[2].record()
             if a.optimizer == "flat":
-                opt.step(bucket.flat)
+                opt.step(bucket)  # the bucket carries its layout; FlatAdam rejects a non-native one
             else:
                 opt.step()
             bucket_bytes, zero_copy = bucket.nbytes(), bucket.zero_copy

@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--module", default=None, help="run one test module in-process (used by the driver mode)")
     ap.add_argument("--per-module-timeout", type=int, default=120)
     ap.add_argument("--modules", default=None, help="comma-separated subset of test modules")
+    ap.add_argument("--same-as", default=None,
+                    help="JSON summary of another --impl run: exit 0 iff this run fails EXACTLY the same tests (the "
+                         "reference's own stale literals fail on the reference build too)")
     args = ap.parse_args()
     names = ["test_projection", "test_tile_culling", "test_rasterize", "test_depth", "test_structs", "test_utils",
              "test_cuda_autograd_functions", "test_rasterize_autograd"]
@@ -46,19 +49,39 @@ def main():
                                     text=True, timeout=args.per_module_timeout)
                 tail = (pr.stdout + pr.stderr)[-1500:]
                 status = "ok" if pr.returncode == 0 else f"rc={pr.returncode}"
+                detail = None
+                for line in reversed(pr.stdout.splitlines()):  # the child's last JSON line names the failing tests
+                    if line.startswith("{") and '"failures"' in line:
+                        detail = json.loads(line)
+                        break
             except subprocess.TimeoutExpired as e:
                 tail = ((e.stdout or b"").decode(errors="ignore") + (e.stderr or b"").decode(errors="ignore"))[-1500:]
                 status = f"TIMEOUT after {args.per_module_timeout}s"
-            summary["modules"][n] = dict(status=status, seconds=round(time.time() - t0, 1), tail=tail)
+                detail = None
+            summary["modules"][n] = dict(status=status, seconds=round(time.time() - t0, 1), tail=tail,
+                                         run=None if detail is None else detail["run"],
+                                         failed=None if detail is None else sorted(detail["failures"] + detail["errors"]))
             print(n, status, f"{time.time() - t0:.1f}s", flush=True)
             if args.out:
                 Path(args.out).parent.mkdir(parents=True, exist_ok=True)
                 Path(args.out).write_text(json.dumps(summary, indent=1))
         summary["ok"] = all(m["status"] == "ok" for m in summary["modules"].values())
         print(json.dumps({k: v["status"] for k, v in summary["modules"].items()}))
+        def failing(sm):
+            return {n: (m.get("failed") if m["status"].startswith("rc=") else m["status"])
+                    for n, m in sm["modules"].items() if m["status"] != "ok"}
+
+        rc = 0 if summary["ok"] else 1
+        if args.same_as:
+            other = json.loads(Path(args.same_as).read_text())
+            summary["same_failures_as"] = dict(file=args.same_as, impl=other.get("impl"),
+                                               identical=failing(other) == failing(summary), mine=failing(summary),
+                                               theirs=failing(other))
+            rc = 0 if summary["same_failures_as"]["identical"] else 1
+            print(json.dumps(summary["same_failures_as"]))
         if args.out:
             Path(args.out).write_text(json.dumps(summary, indent=1))
-        return 0
+        return rc
     names = [args.module]
     import torch  # noqa: F401
 
