@@ -29,6 +29,7 @@ CU_SOURCES = [
     "gsr_render.cu",
     "gsr_render_generic.cu",
     "gsr_adam.cu",
+    "gsr_densify.cu",
 ]
 HEADERS = [
     CSRC / "gsr_common.cuh",

@@ -704,6 +704,67 @@ void densify_accumulate(torch::Tensor vis_idx, torch::Tensor uv_grad, torch::Ten
              "gsr_densify_accumulate");
 }
 
+// the plan of one adaptive-density-control pass applied to the flat parameter buffer and both Adam moments;
+// returns (p_out, m_out, v_out) freshly allocated (m_out / v_out undefined tensors when no moments were given)
+std::vector<torch::Tensor> densify_apply(torch::Tensor p_in, c10::optional<torch::Tensor> m_in,
+                                         c10::optional<torch::Tensor> v_in, int64_t n_in, int64_t n_sh_rest,
+                                         torch::Tensor src, c10::optional<torch::Tensor> clone_row,
+                                         c10::optional<torch::Tensor> split_row, c10::optional<torch::Tensor> xyz_sub,
+                                         c10::optional<torch::Tensor> xyz_add, c10::optional<torch::Tensor> q_set,
+                                         c10::optional<torch::Tensor> scale_set,
+                                         c10::optional<torch::Tensor> p_out_buf) {
+    CHECK_VALID_INPUT(p_in); CHECK_FLOAT_TENSOR(p_in); CHECK_VALID_INPUT(src);
+    TORCH_CHECK(src.scalar_type() == torch::kInt32, "src must be int32");
+    TORCH_CHECK(p_in.numel() == gsr_flat_numel(n_in, (int)n_sh_rest), "p_in does not match the flat layout of n_in gaussians");
+    const int64_t n_out = src.numel();
+    const int64_t total = gsr_flat_numel(n_out, (int)n_sh_rest);
+    const bool moments = m_in.has_value();
+    TORCH_CHECK(moments == v_in.has_value(), "m_in and v_in go together");
+    auto i32ptr = [&](const c10::optional<torch::Tensor>& t, const char* name) -> const int32_t* {
+        if (!t.has_value()) return nullptr;
+        CHECK_VALID_INPUT((*t));
+        TORCH_CHECK(t->scalar_type() == torch::kInt32 && t->numel() == n_out, name, " must be int32 [n_out]");
+        return t->data_ptr<int32_t>();
+    };
+    auto f32ptr = [&](const c10::optional<torch::Tensor>& t) -> const float* {
+        if (!t.has_value() || t->numel() == 0) return nullptr;
+        CHECK_VALID_INPUT((*t)); CHECK_FLOAT_TENSOR((*t));
+        return t->data_ptr<float>();
+    };
+    const int32_t* cr = i32ptr(clone_row, "clone_row");
+    const int32_t* sr = i32ptr(split_row, "split_row");
+    // an index array without its value table means "no such rows": the kernel then must not see the index array
+    const float* sub = f32ptr(xyz_sub);
+    const float* add = f32ptr(xyz_add);
+    const float* qs = f32ptr(q_set);
+    const float* ss = f32ptr(scale_set);
+    if (sub == nullptr) cr = nullptr;
+    if (add == nullptr || qs == nullptr || ss == nullptr) sr = nullptr;
+    c10::cuda::CUDAGuard guard(p_in.device());
+    torch::Tensor p_out;
+    if (p_out_buf.has_value()) {  // caller-owned destination (e.g. symmetric memory)
+        p_out = *p_out_buf;
+        CHECK_VALID_INPUT(p_out); CHECK_FLOAT_TENSOR(p_out);
+        TORCH_CHECK(p_out.numel() == total && p_out.data_ptr() != p_in.data_ptr(), "bad p_out buffer");
+    } else {
+        p_out = torch::empty({total}, p_in.options());
+    }
+    torch::Tensor m_out, v_out;
+    if (moments) {
+        CHECK_VALID_INPUT((*m_in)); CHECK_VALID_INPUT((*v_in)); CHECK_FLOAT_TENSOR((*m_in)); CHECK_FLOAT_TENSOR((*v_in));
+        TORCH_CHECK(m_in->numel() == p_in.numel() && v_in->numel() == p_in.numel(), "moments must match p_in");
+        m_out = torch::empty({total}, p_in.options());
+        v_out = torch::empty({total}, p_in.options());
+    }
+    check_rc(gsr_densify_apply((int)n_in, (int)n_out, (int)n_sh_rest, F32PTR(p_in), moments ? F32PTR((*m_in)) : nullptr,
+                               moments ? F32PTR((*v_in)) : nullptr, src.data_ptr<int32_t>(), cr, sr, sub, add, qs, ss,
+                               F32PTR(p_out), moments ? F32PTR(m_out) : nullptr, moments ? F32PTR(v_out) : nullptr,
+                               cur_stream()),
+             "gsr_densify_apply");
+    if (moments) return {p_out, m_out, v_out};
+    return {p_out};
+}
+
 std::string version() { return gsr_version(); }
 
 }  // namespace
@@ -739,5 +800,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("adam_step_flat", &adam_step_flat, "Adam on the flat parameter buffer");
     m.def("adam_step_sharded", &adam_step_sharded, "reduce-scatter + Adam + all-gather over peer memory");
     m.def("densify_accumulate", &densify_accumulate, "per-step densification statistics");
+    m.def("densify_apply", &densify_apply, "clone / split / delete applied to the flat parameter + Adam buffers");
     m.def("version", &version, "library version string");
 }

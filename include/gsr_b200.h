@@ -281,6 +281,27 @@ int gsr_adam_step_sharded(int64_t lo, int64_t hi, int world, const float* const*
 int gsr_densify_accumulate(int N, int M, const int32_t* vis_idx, float* uv_grad, const float* xyz_grad, const float* K,
                            float* uv_grad_accum, float* xyz_grad_accum, int32_t* grad_accum_count, void* stream);
 
+/* Length (in floats) of the flat parameter / gradient / Adam-moment buffer of n_gaussians gaussians with
+ * n_sh_rest higher-order SH coefficients per channel: sections [xyz 3 | quaternion 4 | scale 3 | opacity 1 |
+ * rgb 3 | sh 3*n_sh_rest], every section start 16-byte aligned (the layout gsr_preprocess_backward writes). */
+int64_t gsr_flat_numel(int64_t n_gaussians, int n_sh_rest);
+
+/* Clone / split / delete of the reference's adaptive density control (splat_py/trainer.py:114-206 with the
+ * optimizer surgery of splat_py/optimizer_manager.py:74-172), applied to the flat parameter buffer and both Adam
+ * moment buffers in ONE pass.  The plan is per OUTPUT row r (n_out rows):
+ *   src[r]        row of the old buffers (n_in rows) it is copied from
+ *   clone_row[r]  >= 0: a clone, xyz -= xyz_sub[clone_row[r]][0..2]            (trainer.py:122-126); else -1
+ *   split_row[r]  >= 0: a split sample, xyz += xyz_add[...], quaternion = q_set[...], scale = scale_set[...]
+ *                 (trainer.py:166-194); else -1
+ * Rows with clone_row >= 0 or split_row >= 0 are new: their Adam moments are zero; all others keep their source
+ * row's moments.  clone_row / split_row may be NULL (no clones / no splits); m_in, v_in, m_out, v_out may all be
+ * NULL (parameters only).  p_out / m_out / v_out: caller-allocated, gsr_flat_numel(n_out, n_sh_rest) floats,
+ * must not alias the inputs.  Deletion is expressed by src skipping the deleted rows. */
+int gsr_densify_apply(int n_in, int n_out, int n_sh_rest, const float* p_in, const float* m_in, const float* v_in,
+                      const int32_t* src, const int32_t* clone_row, const int32_t* split_row, const float* xyz_sub,
+                      const float* xyz_add, const float* q_set, const float* scale_set, float* p_out, float* m_out,
+                      float* v_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

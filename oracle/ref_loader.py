@@ -41,20 +41,24 @@ def _load_ref_ext():
     return _cache["ext"]
 
 
-def _import_reference_package(cuda_module, alias: str):
+def _import_reference_package(cuda_module, alias: str, submodules=_SUBMODULES, extra_path=None):
     """Import oracle/_ref/splat_py with `splat_cuda` bound to `cuda_module`; register it as `alias`."""
     saved = {k: v for k, v in sys.modules.items() if k == "splat_cuda" or k == "splat_py" or k.startswith("splat_py.")}
     for k in saved:
         del sys.modules[k]
     sys.modules["splat_cuda"] = cuda_module
     sys.path.insert(0, str(REF_DIR))
+    if extra_path:
+        sys.path.insert(0, str(extra_path))
     try:
         pkg = importlib.import_module("splat_py")
-        for sub in _SUBMODULES:
+        for sub in submodules:
             importlib.import_module(f"splat_py.{sub}")
         loaded = {k: v for k, v in sys.modules.items() if k == "splat_py" or k.startswith("splat_py.")}
     finally:
         sys.path.remove(str(REF_DIR))
+        if extra_path:
+            sys.path.remove(str(extra_path))
         for k in [k for k in sys.modules if k == "splat_cuda" or k == "splat_py" or k.startswith("splat_py.")]:
             del sys.modules[k]
         sys.modules.update(saved)
@@ -80,3 +84,20 @@ def load_reference_on_b200():
 
         _cache["on_b200"] = _import_reference_package(g.native(), "splat_py_on_b200")
     return _cache["on_b200"]
+
+
+def load_reference_trainer():
+    """The reference's trainer / optimizer-manager / config modules (splat_py/trainer.py etc.), imported with
+    THIS library's `splat_cuda` underneath (the trainer's densification code does not touch CUDA kernels) and the
+    stand-ins for the two packages the image lacks (tools/e2e/shims: torchmetrics SSIM, plotext).  Registered as
+    `splat_py_trainer_ref.*`.  Used by tests/test_densify_gpu.py as the checker of the flat-buffer densification."""
+    if "trainer" not in _cache:
+        if not (REF_DIR / "splat_py" / "trainer.py").exists():
+            raise ImportError("oracle/_ref/splat_py is not installed")
+        import gaussian_splatting_b200 as g
+
+        shims = Path(__file__).resolve().parent.parent / "tools" / "e2e" / "shims"
+        _cache["trainer"] = _import_reference_package(
+            g.native(), "splat_py_trainer_ref", submodules=_SUBMODULES + ("config", "optimizer_manager", "trainer"),
+            extra_path=shims)
+    return _cache["trainer"]

@@ -1,0 +1,107 @@
+"""Which arithmetic does torch.linalg.inv_ex (cuSOLVER getrf + cuBLAS trsm, batch of one 4x4 fp32 matrix) perform?
+The fused rasterizer needs inverse(camera_T_world)[:3, 3] (the camera centre, splat_py/rasterize.py:91-93) with the
+reference's bits; torch's chain is 15 micro-kernels.  This probe evaluates candidate fp32 operation orders of a 4x4
+partial-pivot LU + two triangular solves in numpy (FMA emulated through float64) against torch on the GPU for many
+rigid and general poses and reports which candidates reproduce column 3 of the inverse bit for bit."""
+import itertools
+import json
+import sys
+
+import numpy as np
+import torch
+
+f32 = np.float32
+
+
+def fma(a, b, c):
+    return f32(np.float64(a) * np.float64(b) + np.float64(c))
+
+
+def lu_solve_col3(A, div_l, fma_upd, lower_fma, upper_mode, upper_fma):
+    """column 3 of inv(A).  Variants:
+    div_l      True: l = a/p ; False: l = a * (1/p)
+    fma_upd    True: a_ij = fma(-l, a_kj, a_ij) ; False: a_ij = a_ij - l*a_kj
+    lower_fma  True: y_i accumulates with fma(-l_ij, y_j, acc) ; False: acc - l*y
+    upper_mode 'div': x_i = acc / u_ii ; 'rcp': x_i = acc * (1/u_ii)
+    upper_fma  like lower_fma for the back substitution"""
+    A = A.astype(f32).copy()
+    n = 4
+    perm = list(range(n))
+    for k in range(n):
+        piv = k + int(np.argmax(np.abs(A[k:, k])))
+        if piv != k:
+            A[[k, piv]] = A[[piv, k]]
+            perm[k], perm[piv] = perm[piv], perm[k]
+        p = A[k, k]
+        rp = f32(1.0) / p
+        for i in range(k + 1, n):
+            l = f32(A[i, k] / p) if div_l else f32(A[i, k] * rp)
+            A[i, k] = l
+            for j in range(k + 1, n):
+                A[i, j] = fma(-l, A[k, j], A[i, j]) if fma_upd else f32(A[i, j] - f32(l * A[k, j]))
+    b = np.zeros(n, f32)
+    b[3] = 1.0
+    b = b[perm]
+    y = np.zeros(n, f32)
+    for i in range(n):
+        acc = b[i]
+        for j in range(i):
+            acc = fma(-A[i, j], y[j], acc) if lower_fma else f32(acc - f32(A[i, j] * y[j]))
+        y[i] = acc
+    x = np.zeros(n, f32)
+    for i in range(n - 1, -1, -1):
+        acc = y[i]
+        for j in range(i + 1, n):
+            acc = fma(-A[i, j], x[j], acc) if upper_fma else f32(acc - f32(A[i, j] * x[j]))
+        x[i] = f32(acc / A[i, i]) if upper_mode == "div" else f32(acc * (f32(1.0) / A[i, i]))
+    return x[:3]
+
+
+def poses(n, rng, general):
+    out = []
+    for _ in range(n):
+        if general:
+            T = np.eye(4)
+            T[:3, :] = rng.standard_normal((3, 4))
+        else:
+            q = rng.standard_normal(4)
+            q /= np.linalg.norm(q)
+            w, x, y, z = q
+            T = np.eye(4)
+            T[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+            T[:3, 3] = rng.standard_normal(3) * 3
+        out.append(T.astype(f32))
+    return out
+
+
+def main():
+    out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/inverse_probe.json"
+    rng = np.random.default_rng(0)
+    mats = poses(600, rng, False) + poses(200, rng, True)
+    from gaussian_splatting_b200 import synth
+
+    mats += [synth.make_pose(v, 8).numpy() for v in range(8)]
+    dev = torch.device("cuda:0")
+    ref = [torch.linalg.inv_ex(torch.from_numpy(M).to(dev))[0][:3, 3].cpu().numpy() for M in mats]
+    ref2 = [torch.inverse(torch.from_numpy(M).to(dev))[:3, 3].cpu().numpy() for M in mats]
+    same_inv = sum(int((a.view(np.int32) == b.view(np.int32)).all()) for a, b in zip(ref, ref2))
+    results = []
+    for div_l, fma_upd, lower_fma, upper_mode, upper_fma in itertools.product(
+            (True, False), (True, False), (True, False), ("div", "rcp"), (True, False)):
+        ok = 0
+        for M, r in zip(mats, ref):
+            c = lu_solve_col3(M, div_l, fma_upd, lower_fma, upper_mode, upper_fma)
+            ok += int((c.view(np.int32) == r.view(np.int32)).all())
+        results.append(dict(div_l=div_l, fma_upd=fma_upd, lower_fma=lower_fma, upper_mode=upper_mode,
+                            upper_fma=upper_fma, match=ok, of=len(mats)))
+    results.sort(key=lambda d: -d["match"])
+    json.dump(dict(inv_ex_equals_inverse=same_inv, n=len(mats), candidates=results), open(out, "w"), indent=1)
+    print("inv_ex == inverse:", same_inv, "/", len(mats))
+    for r in results[:6]:
+        print(r)
+
+
+if __name__ == "__main__":
+    main()
