@@ -313,7 +313,7 @@ void render_tiles_cuda(torch::Tensor uvs, torch::Tensor opacity, torch::Tensor r
         check_rc(gsr_render_forward(records.data_ptr<float>(), splat_start_end_idx_by_tile_idx.data_ptr<int>(),
                                     background_rgb.data_ptr<float>(), s.H, s.W,
                                     num_splats_per_pixel.data_ptr<int>(), final_weight_per_pixel.data_ptr<float>(),
-                                    rendered_image.data_ptr<float>(), cur_stream()),
+                                    rendered_image.data_ptr<float>(), nullptr, cur_stream()),
                  "gsr_render_forward");
     } else {
         check_rc(gsr_render_forward_generic(
@@ -363,7 +363,7 @@ void render_tiles_backward_cuda(torch::Tensor uvs, torch::Tensor opacity, torch:
                                      num_splats_per_pixel.data_ptr<int>(), final_weight_per_pixel.data_ptr<float>(),
                                      grad_image.data_ptr<float>(), grad_rgb.data_ptr<float>(),
                                      grad_opacity.data_ptr<float>(), grad_uvs.data_ptr<float>(),
-                                     grad_conic.data_ptr<float>(), cur_stream()),
+                                     grad_conic.data_ptr<float>(), nullptr, cur_stream()),
                  "gsr_render_backward");
     } else {
         check_rc(gsr_render_backward_generic(
@@ -525,11 +525,10 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
     return std::make_tuple(ids_sorted.narrow(0, 0, P), ranges, stream_rec, vis_idx, uv);
 }
 
-// image [H,W,3], n [H,W] i32, wlast [H,W]
-std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> fused_render_forward(torch::Tensor stream_rec,
-                                                                             torch::Tensor ranges,
-                                                                             torch::Tensor background, int64_t H,
-                                                                             int64_t W) {
+// image [H,W,3], n [H,W] i32, wlast [H,W], contribution masks (i32 words; empty when record_masks is false)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_render_forward(
+    torch::Tensor stream_rec, torch::Tensor ranges, torch::Tensor background, int64_t H, int64_t W, int64_t P,
+    bool record_masks) {
     CHECK_VALID_INPUT(background); CHECK_FLOAT_TENSOR(background);
     TORCH_CHECK(background.numel() == 3, "Background RGB must have 3 elements");
     c10::cuda::CUDAGuard guard(stream_rec.device());
@@ -537,17 +536,21 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> fused_render_forward(tor
     torch::Tensor image = torch::empty({H, W, 3}, opt);
     torch::Tensor n = torch::empty({H, W}, opt.dtype(torch::kInt32));
     torch::Tensor w = torch::empty({H, W}, opt);
+    torch::Tensor masks = record_masks
+                              ? torch::zeros({(int64_t)gsr_contribution_mask_words(P, (int)H, (int)W)}, opt.dtype(torch::kInt32))
+                              : torch::empty({0}, opt.dtype(torch::kInt32));
     check_rc(gsr_render_forward(F32PTR(stream_rec), ranges.data_ptr<int>(), F32PTR(background), (int)H, (int)W,
-                                n.data_ptr<int>(), F32PTR(w), F32PTR(image), cur_stream()),
+                                n.data_ptr<int>(), F32PTR(w), F32PTR(image),
+                                record_masks ? (uint32_t*)masks.data_ptr<int>() : nullptr, cur_stream()),
              "gsr_render_forward");
-    return std::make_tuple(image, n, w);
+    return std::make_tuple(image, n, w, masks);
 }
 
 // per-gaussian gradient slab, flat [9N]: rgb [N,3] | opacity [N] | uv [N,2] | conic [N,3], rows indexed
 // by ORIGINAL gaussian index; zero-filled, then accumulated into by the render backward
 torch::Tensor fused_render_backward(torch::Tensor grad_image, int64_t N, torch::Tensor stream_rec,
                                     torch::Tensor ids_sorted, torch::Tensor ranges, torch::Tensor background,
-                                    torch::Tensor n, torch::Tensor w) {
+                                    torch::Tensor n, torch::Tensor w, torch::Tensor masks) {
     CHECK_VALID_INPUT(grad_image); CHECK_FLOAT_TENSOR(grad_image);
     const int H = n.size(0), W = n.size(1);
     TORCH_CHECK(grad_image.dim() == 3 && grad_image.size(0) == H && grad_image.size(1) == W &&
@@ -561,7 +564,8 @@ torch::Tensor fused_render_backward(torch::Tensor grad_image, int64_t N, torch::
     float* g_conic = g_uv + (size_t)N * 2;
     check_rc(gsr_render_backward(F32PTR(stream_rec), ids_sorted.data_ptr<int>(), ranges.data_ptr<int>(),
                                  F32PTR(background), H, W, n.data_ptr<int>(), F32PTR(w), F32PTR(grad_image),
-                                 g_rgb, g_opa, g_uv, g_conic, cur_stream()),
+                                 g_rgb, g_opa, g_uv, g_conic,
+                                 masks.numel() > 0 ? (const uint32_t*)masks.data_ptr<int>() : nullptr, cur_stream()),
              "gsr_render_backward");
     return slab;
 }

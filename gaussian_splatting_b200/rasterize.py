@@ -43,6 +43,9 @@ import os
 # N in {2000 ... 3M}); below IN_KERNEL_TRANSFORM_MIN_N, or with GSR_TORCH_TRANSFORM=1, positions are formed by
 # torch.matmul exactly as the reference does (splat_py/utils.py:60-72).
 IN_KERNEL_TRANSFORM = os.environ.get("GSR_TORCH_TRANSFORM", "0") != "1"
+# the forward records which (8x4 pixel block, splat) pairs contributed; the backward then visits exactly those
+# (GSR_NO_MASKS=1: the backward redoes the forward's conservative footprint test instead)
+USE_CONTRIBUTION_MASKS = os.environ.get("GSR_NO_MASKS", "0") != "1"
 IN_KERNEL_TRANSFORM_MIN_N = 16384
 CUBLAS_BATCH_CHUNK = 65535   # gridDim limit cuBLAS batches against
 SMALL_BATCH = 1024           # chunks below ~300 use another kernel (measured: 100 differs, 300 matches)
@@ -121,7 +124,7 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
-                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "vis_idx32", "scan")
+                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "vis_idx32", "scan", "masks")
 
     def __init__(self, profile=None):
         self.profile = profile  # optional list: (stage name, start event, end event) per native call
@@ -224,9 +227,11 @@ class _CompositeTiles(torch.autograd.Function):
     @staticmethod
     def forward(ctx, uv, carrier, background_rgb, state):
         with _stage(state, "render_fwd"):
-            image, n_pp, w_pp = native().fused_render_forward(state.stream_rec, state.ranges, background_rgb,
-                                                              state.H, state.W)
-        state.n_per_pixel, state.w_per_pixel, state.background = n_pp, w_pp, background_rgb
+            # contribution masks are recorded only when a backward pass can follow
+            image, n_pp, w_pp, masks = native().fused_render_forward(
+                state.stream_rec, state.ranges, background_rgb, state.H, state.W, state.P,
+                USE_CONTRIBUTION_MASKS and any(ctx.needs_input_grad[:2]))
+        state.n_per_pixel, state.w_per_pixel, state.background, state.masks = n_pp, w_pp, background_rgb, masks
         ctx.state = state
         return image
 
@@ -235,7 +240,7 @@ class _CompositeTiles(torch.autograd.Function):
         st = ctx.state
         with _stage(st, "render_bwd"):
             slab = native().fused_render_backward(grad_image.contiguous(), st.N, st.stream_rec, st.ids_sorted,
-                                                  st.ranges, st.background, st.n_per_pixel, st.w_per_pixel)
+                                                  st.ranges, st.background, st.n_per_pixel, st.w_per_pixel, st.masks)
         N = st.N
         grad_uv = slab[4 * N:6 * N].view(N, 2).index_select(0, st.vis_idx)
         return grad_uv, slab, None, None

@@ -130,19 +130,29 @@ int gsr_pack_records(int P, const int32_t* sorted_gaussian_idx, const float* uvs
                      const float* opacity, const float* rgb, const float* conic, float* records,
                      void* stream);
 
+/* Number of 32-bit words of the forward -> backward contribution masks for a stream of P records on an H x W
+ * image: per (tile, 128-record batch, warp, lane group) one 128-bit mask of the batch's records that contributed
+ * to at least one pixel of the group's 8x4 pixel block. */
+size_t gsr_contribution_mask_words(int64_t P, int H, int W);
+
 /* records [P,12], tile_ranges [n_tiles+1], background [3] ->
- * image [H,W,3], num_splats_per_pixel int32 [H,W], final_weight_per_pixel [H,W] */
+ * image [H,W,3], num_splats_per_pixel int32 [H,W], final_weight_per_pixel [H,W].
+ * contribution_masks: NULL, or gsr_contribution_mask_words(P, H, W) ZERO-FILLED words the kernel records the
+ * contributing (pixel block, record) pairs in, for gsr_render_backward of the same view. */
 int gsr_render_forward(const float* records, const int32_t* tile_ranges, const float* background_rgb,
                        int H, int W, int32_t* num_splats_per_pixel, float* final_weight_per_pixel,
-                       float* image, void* stream);
+                       float* image, uint32_t* contribution_masks, void* stream);
 
 /* + grad_image [H,W,3]; accumulates into grad_rgb [N,3], grad_opacity [N], grad_uv [N,2],
- * grad_conic [N,3] at row sorted_gaussian_idx[p] */
+ * grad_conic [N,3] at row sorted_gaussian_idx[p].
+ * contribution_masks: NULL (the kernel finds the candidate records of every pixel block with its own
+ * conservative footprint test, like the forward), or the masks the forward of this view recorded: the backward
+ * then visits exactly the (pixel block, record) pairs that contributed. */
 int gsr_render_backward(const float* records, const int32_t* sorted_gaussian_idx,
                         const int32_t* tile_ranges, const float* background_rgb, int H, int W,
                         const int32_t* num_splats_per_pixel, const float* final_weight_per_pixel,
                         const float* grad_image, float* grad_rgb, float* grad_opacity,
-                        float* grad_uv, float* grad_conic, void* stream);
+                        float* grad_uv, float* grad_conic, const uint32_t* contribution_masks, void* stream);
 
 /* General renderers: any dtype, any n_sh in {1,4,9,16} (per-pixel SH via view_dir_by_pixel
  * [H,W,3]); same semantics as the reference's template instantiations

@@ -51,7 +51,7 @@ def test_library_is_sm100a_only_and_has_tma():
     elfs = subprocess.run(["cuobjdump", "-lelf", str(so)], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", elfs))
     assert archs == {"100a"}, archs
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3gsr12k_render_fwdEPKfPKiS1_iiPiPfS5_", str(so)],
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3gsr12k_render_fwdILb1EEEvPKfPKiS2_iiPiPfS6_Pj", str(so)],
                           capture_output=True, text=True).stdout
     assert "UBLKCP" in sass, "render forward kernel should stage records with TMA bulk copies (UBLKCP)"
 

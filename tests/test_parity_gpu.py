@@ -390,6 +390,26 @@ def test_live_reference_per_pixel_sh_backward_fp32():
         assert rel(mine[k], v) < REL_TOL, (k, rel(mine[k], v))
 
 
+def test_contribution_masks_do_not_change_the_gradients():
+    """The forward records which (8x4 pixel block, splat) pairs contributed and the backward visits only those;
+    without the masks (GSR_NO_MASKS=1) the backward walks the forward's conservative candidate lists.  Same
+    gradients either way (atomics noise), same image bits."""
+    from gaussian_splatting_b200 import rasterize as R
+
+    sc = scenes.np_scene(60_000, "720p", sh_degree=2, seed=4, view=1, n_views=3)
+    G = synth.make_upstream_grad("720p").numpy()
+    assert R.USE_CONTRIBUTION_MASKS
+    with_masks = run_b200(sc, G=G)
+    R.USE_CONTRIBUTION_MASKS = False
+    try:
+        without = run_b200(sc, G=G)
+    finally:
+        R.USE_CONTRIBUTION_MASKS = True
+    assert_bits_equal(with_masks["image"], without["image"], "image")
+    for k in ("g_xyz", "g_rgb", "g_opacity", "g_scale", "g_quaternion", "g_sh", "g_uv"):
+        assert rel(with_masks[k], without[k]) < 2e-6, (k, rel(with_masks[k], without[k]))
+
+
 def test_in_kernel_transform_self_check_passes_on_this_device():
     """rasterize() verifies once per device that the in-kernel world->camera transform still reproduces
     torch.matmul bit for bit (and falls back to torch.matmul itself otherwise); on the pinned torch / cuBLAS of

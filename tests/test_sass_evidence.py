@@ -39,7 +39,7 @@ def find(counts, fragment):
 def test_tile_kernels_use_packed_fp32_and_tma():
     counts = sass_counts()
     for k in ("k_render_fwd", "k_render_bwd"):
-        c = find(counts, f"gsr{len(k)}{k}E")  # itanium mangling: N3gsr<len><name>E
+        c = find(counts, f"gsr{len(k)}{k}ILb1E")  # itanium mangling: N3gsr<len><name>I<template args>E (masks on)
         assert c["FFMA2"] >= 10 and c["FMUL2"] >= 10, (k, dict(c))      # two pixels per lane, packed arithmetic
         assert c["UBLKCP"] >= 1 and c["SYNCS"] >= 1, (k, dict(c))        # record batches arrive by TMA + mbarrier
         assert c["BAR"] <= 4, (k, dict(c))                               # no CTA barrier in the batch loops (setup only)

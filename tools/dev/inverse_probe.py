@@ -7,8 +7,12 @@ import itertools
 import json
 import sys
 
+from pathlib import Path
+
 import numpy as np
 import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 
 f32 = np.float32
 
