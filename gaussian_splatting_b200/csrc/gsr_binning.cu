@@ -139,23 +139,27 @@ __global__ void __launch_bounds__(BIN_THREADS) k_ids_to_i32(int P, const uint32_
 // one 48-byte record per pair, three 16-byte lanes per record: thread -> (pair, lane)
 __global__ void __launch_bounds__(BIN_THREADS)
     k_gather_records(int P, const uint32_t* __restrict__ ids, const float4* __restrict__ rec,
-                     float4* __restrict__ out) {
+                     float4* __restrict__ out, const uint64_t* __restrict__ scan, int32_t* __restrict__ rank_out) {
     const int64_t t = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x;
     if (t >= (int64_t)P * 3) return;
     const int p = (int)(t / 3), lane = (int)(t % 3);
-    out[t] = __ldg(rec + (size_t)ids[p] * 3 + lane);
+    const uint32_t id = ids[p];
+    if (lane == 0 && rank_out != nullptr) rank_out[p] = (int32_t)(scan[id] >> 32) - 1;
+    out[t] = __ldg(rec + (size_t)id * 3 + lane);
 }
 
-// same, ids taken from the low id_bits of the sorted keys; also writes them out for the backward's flush
+// same, ids taken from the low id_bits of the sorted keys; also writes, for the backward's flush, the row of the
+// per-gaussian gradient arrays each pair accumulates into: the gaussian id, or — when the packed scan of the
+// per-gaussian stage is given — its RANK among the visible gaussians (compact gradient arrays of M rows)
 __global__ void __launch_bounds__(BIN_THREADS)
     k_gather_records_keys(int P, const uint64_t* __restrict__ keys, uint64_t id_mask,
                           const float4* __restrict__ rec, float4* __restrict__ out,
-                          int32_t* __restrict__ ids_out) {
+                          int32_t* __restrict__ ids_out, const uint64_t* __restrict__ scan) {
     const int64_t t = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x;
     if (t >= (int64_t)P * 3) return;
     const int p = (int)(t / 3), lane = (int)(t % 3);
     const uint32_t id = (uint32_t)(keys[p] & id_mask);
-    if (lane == 0) ids_out[p] = (int32_t)id;
+    if (lane == 0) ids_out[p] = (scan != nullptr) ? (int32_t)(scan[id] >> 32) - 1 : (int32_t)id;
     out[t] = __ldg(rec + (size_t)id * 3 + lane);
 }
 
@@ -313,18 +317,20 @@ int gsr_sort_keys(int P, int n_tiles, int depth_bits, int id_bits, const uint64_
 }
 
 int gsr_gather_records_keys(int P, int id_bits, const uint64_t* keys_sorted, const float* records, float* out,
-                            int32_t* ids_sorted, void* stream) {
+                            int32_t* ids_sorted, const uint64_t* scan, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (P <= 0) return GSR_OK;
     k_gather_records_keys<<<BGRID((int64_t)P * 3)>>>(P, keys_sorted, (((uint64_t)1) << id_bits) - 1,
-                                                     (const float4*)records, (float4*)out, ids_sorted);
+                                                     (const float4*)records, (float4*)out, ids_sorted, scan);
     return (int)cudaGetLastError();
 }
 
-int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, float* out, void* stream) {
+int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, float* out, const uint64_t* scan,
+                       int32_t* ranks_sorted, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (P <= 0) return GSR_OK;
-    k_gather_records<<<BGRID((int64_t)P * 3)>>>(P, ids_sorted, (const float4*)records, (float4*)out);
+    if ((scan == nullptr) != (ranks_sorted == nullptr)) return GSR_ERR_BAD_ARG;
+    k_gather_records<<<BGRID((int64_t)P * 3)>>>(P, ids_sorted, (const float4*)records, (float4*)out, scan, ranks_sorted);
     return (int)cudaGetLastError();
 }
 

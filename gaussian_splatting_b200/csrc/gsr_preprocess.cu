@@ -31,33 +31,70 @@ struct ViewConsts {
     float cam[3];  // camera centre in world frame = inverse(camera_T_world)[:3, 3]
 };
 
-// last column of inverse(T) by Gauss-Jordan with partial pivoting in fp64 (one thread)
+// Last column of inverse(T) with the bits torch.inverse / torch.linalg.inv_ex produce on this platform for one 4x4
+// fp32 matrix (the reference's op, splat_py/rasterize.py:91-93).  torch runs cuSOLVER getrf + cuBLAS trsm x2 — 15
+// micro-kernels; their arithmetic was pinned on a B200 by tools/dev/inverse_probe2.py (600 of 600 random rigid and
+// general matrices bit-identical, LU factors and solution separately):
+//   LU, partial pivoting (first maximum):  l_ik = a_ik * (1 / a_kk)   [IEEE reciprocal, then a multiply]
+//                                          a_ij = fma(-l_ik, a_kj, a_ij)
+//   L y = P e_3 forward, fma accumulation;  U x = y by columns from the last one (right-looking: the terms of a row
+//   are subtracted in DESCENDING column order), fma accumulation, then one IEEE division by the diagonal.
+// One thread; ~100 flops.
 __device__ void camera_centre(const float* __restrict__ T, float* __restrict__ cam) {
-    double A[4][5];
-    for (int r = 0; r < 4; ++r) {
-        for (int c = 0; c < 4; ++c) A[r][c] = (double)T[r * 4 + c];
-        A[r][4] = (r == 3) ? 1.0 : 0.0;
-    }
-    for (int col = 0; col < 4; ++col) {
-        int piv = col;
-        for (int r = col + 1; r < 4; ++r)
-            if (fabs(A[r][col]) > fabs(A[piv][col])) piv = r;
-        for (int c = 0; c < 5; ++c) {
-            const double t = A[col][c];
-            A[col][c] = A[piv][c];
-            A[piv][c] = t;
+    float A[4][4];
+    int perm[4] = {0, 1, 2, 3};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) A[r][c] = T[r * 4 + c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int piv = k;
+        float best = fabsf(A[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < 4; ++r) {
+            const float v = fabsf(A[r][k]);
+            if (v > best) { best = v; piv = r; }
         }
-        const double inv = 1.0 / A[col][col];
-        for (int c = 0; c < 5; ++c) A[col][c] *= inv;
-        for (int r = 0; r < 4; ++r) {
-            if (r == col) continue;
-            const double f = A[r][col];
-            for (int c = 0; c < 5; ++c) A[r][c] -= f * A[col][c];
+#pragma unroll
+        for (int r = k + 1; r < 4; ++r) {  // swap rows k and piv without dynamic indexing
+            if (r == piv) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const float t = A[k][c]; A[k][c] = A[r][c]; A[r][c] = t; }
+                const int tp = perm[k]; perm[k] = perm[r]; perm[r] = tp;
+            }
+        }
+        const float rp = __frcp_rn(A[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < 4; ++i) {
+            const float l = __fmul_rn(A[i][k], rp);
+            A[i][k] = l;
+#pragma unroll
+            for (int c = k + 1; c < 4; ++c) A[i][c] = __fmaf_rn(-l, A[k][c], A[i][c]);
         }
     }
-    cam[0] = (float)A[0][4];
-    cam[1] = (float)A[1][4];
-    cam[2] = (float)A[2][4];
+    float y[4], x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float acc = (perm[i] == 3) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int c = 0; c < i; ++c) acc = __fmaf_rn(-A[i][c], y[c], acc);
+        y[i] = acc;
+    }
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+        float acc = y[i];
+#pragma unroll
+        for (int c = 3; c > i; --c) acc = __fmaf_rn(-A[i][c], x[c], acc);
+        x[i] = __fdiv_rn(acc, A[i][i]);
+    }
+    cam[0] = x[0];
+    cam[1] = x[1];
+    cam[2] = x[2];
+}
+
+__global__ void k_camera_centre(const float* __restrict__ T, float* __restrict__ cam) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) camera_centre(T, cam);
 }
 
 // Whole CTA: threads 0..27 fetch one constant each (one memory latency instead of 28 dependent-issue loads by a
@@ -235,8 +272,8 @@ __global__ void __launch_bounds__(PRE_THREADS, 6)
                      const float* __restrict__ camdev, const uint8_t* __restrict__ visible,
                      const float* __restrict__ g_rgb,
                      const float* __restrict__ g_opa, const float* __restrict__ g_uv,
-                     const float* __restrict__ g_conic, const float* __restrict__ g_uv_compact,
-                     const uint64_t* __restrict__ scan, float* __restrict__ o_xyz,
+                     const float* __restrict__ g_conic, const uint64_t* __restrict__ scan,
+                     float* __restrict__ o_xyz,
                      float* __restrict__ o_quat, float* __restrict__ o_scale, float* __restrict__ o_opa,
                      float* __restrict__ o_dc, float* __restrict__ o_sh, int use_tma) {
     constexpr int NR = N_SH - 1;
@@ -268,16 +305,13 @@ __global__ void __launch_bounds__(PRE_THREADS, 6)
         qw = quat[i * 4 + 0]; qx = quat[i * 4 + 1]; qy = quat[i * 4 + 2]; qz = quat[i * 4 + 3];
         s0 = scale[i * 3 + 0]; s1 = scale[i * 3 + 1]; s2 = scale[i * 3 + 2];
         opl = opa_logit[i];
-        gcv[0] = g_conic[i * 3 + 0]; gcv[1] = g_conic[i * 3 + 1]; gcv[2] = g_conic[i * 3 + 2];
-        if (g_uv_compact != nullptr) {  // total gradient on the compact uv [M,2]: row = rank among the visible
-            const size_t row = (size_t)(scan[i] >> 32) - 1;
-            const float2 t = *reinterpret_cast<const float2*>(g_uv_compact + row * 2);
-            guv[0] = t.x; guv[1] = t.y;
-        } else {
-            guv[0] = g_uv[i * 2 + 0]; guv[1] = g_uv[i * 2 + 1];
-        }
-        gov = g_opa[i];
-        grv[0] = g_rgb[i * 3 + 0]; grv[1] = g_rgb[i * 3 + 1]; grv[2] = g_rgb[i * 3 + 2];
+        // row of this gaussian in the incoming gradient arrays: itself, or (compact arrays of M rows) its rank
+        // among the visible gaussians, read off the forward's packed inclusive scan
+        const size_t r = (scan != nullptr) ? (size_t)(scan[i] >> 32) - 1 : (size_t)i;
+        gcv[0] = g_conic[r * 3 + 0]; gcv[1] = g_conic[r * 3 + 1]; gcv[2] = g_conic[r * 3 + 2];
+        guv[0] = g_uv[r * 2 + 0]; guv[1] = g_uv[r * 2 + 1];
+        gov = g_opa[r];
+        grv[0] = g_rgb[r * 3 + 0]; grv[1] = g_rgb[r * 3 + 1]; grv[2] = g_rgb[r * 3 + 2];
     }
     load_view_cta(Tdev, Kdev, camdev, vc, HAS_SH);
     if (vis) {
@@ -363,6 +397,12 @@ using namespace gsr;
 
 extern "C" {
 
+int gsr_camera_centre(const float* camera_T_world, float* centre, void* stream) {
+    if (camera_T_world == nullptr || centre == nullptr) return GSR_ERR_BAD_ARG;
+    k_camera_centre<<<1, 32, 0, (cudaStream_t)stream>>>(camera_T_world, centre);
+    return (int)cudaGetLastError();
+}
+
 size_t gsr_preprocess_temp_bytes(int N) {
     size_t b = 0;
     cub::DeviceScan::InclusiveSum((void*)nullptr, b, (uint64_t*)nullptr, (uint64_t*)nullptr, N > 0 ? N : 1);
@@ -409,12 +449,10 @@ int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float*
                             const float* K, const float* camera_centre, const uint8_t* visible,
                             const float* grad_rgb,
                             const float* grad_opacity, const float* grad_uv, const float* grad_conic,
-                            const float* grad_uv_compact, const uint64_t* scan,
-                            float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
+                            const uint64_t* scan, float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
                             float* g_rgb_dc, float* g_sh_rest, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
-    if (grad_uv_compact != nullptr && scan == nullptr) return GSR_ERR_BAD_ARG;
     const dim3 grid((N + PRE_THREADS - 1) / PRE_THREADS), block(PRE_THREADS);
     const int use_tma = (aligned16(g_xyz) && aligned16(g_quaternion) && aligned16(g_scale) &&
                          aligned16(g_opacity_logit) && aligned16(g_rgb_dc) &&
@@ -424,7 +462,7 @@ int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float*
 #define GSR_PRE_ARGS                                                                                   \
     N, xyz, quaternion, scale, opacity_logit, camera_T_world, K, camera_centre, visible, grad_rgb,         \
         grad_opacity, grad_uv,                                                                             \
-        grad_conic, grad_uv_compact, scan, g_xyz, g_quaternion, g_scale, g_opacity_logit, g_rgb_dc, g_sh_rest, use_tma
+        grad_conic, scan, g_xyz, g_quaternion, g_scale, g_opacity_logit, g_rgb_dc, g_sh_rest, use_tma
     switch (n_sh_rest) {
         case 0: k_preprocess_bwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
         case 3: k_preprocess_bwd<4, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;

@@ -10,9 +10,9 @@ Implementation: two autograd nodes around the native fused kernels
     _ProjectGaussians   params -> uv [M,2], carrier          (gsr_preprocess_forward + binning)
     _CompositeTiles     uv, carrier -> image                  (gsr_render_forward)
 
-``carrier`` is an uninitialised [9N] tensor that only carries gradient: the render backward
-returns its per-Gaussian sums (rgb, opacity, uv, conic) as the carrier's gradient, and the
-per-Gaussian backward consumes them.  One host sync per forward (to size the pair buffers);
+``carrier`` is an uninitialised [9M] tensor that only carries gradient: the render backward
+returns its per-Gaussian sums (rgb, opacity, uv, conic; one row per VISIBLE gaussian, in the order of
+the compact uv) as the carrier's gradient, and the per-Gaussian backward consumes them.  One host sync per forward (to size the pair buffers);
 the reference path has ~25.
 
 ``use_sh_precompute=False`` (per-pixel view directions) is routed through the operator-by-operator
@@ -102,6 +102,47 @@ def in_kernel_transform_ok(device, n: int = 70_000, seed: int = 1234) -> bool:
     return same
 
 
+_CENTRE_OK = {}  # device index -> bool: does gsr_camera_centre reproduce torch's inverse on this device?
+
+
+def native_centre_ok(device, n: int = 24, seed: int = 4321) -> bool:
+    """One-time self-check per device: the camera centre from the library's single kernel (the arithmetic of
+    cuSOLVER getrf + cuBLAS trsm as pinned on a B200, csrc/gsr_preprocess.cu `camera_centre`) against
+    torch.linalg.inv_ex, BIT FOR BIT, on `n` random rigid poses and a few general matrices.  A cuSOLVER / cuBLAS
+    upgrade that changes the rounding order makes rasterize() use torch's own inverse again (15 micro-kernels)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ok = _CENTRE_OK.get(idx)
+    if ok is not None:
+        return ok
+    import warnings
+
+    ext = native()
+    gen = torch.Generator().manual_seed(seed)
+    same = True
+    with torch.no_grad():
+        for k in range(n):
+            if k % 4 == 3:
+                T = torch.eye(4)
+                T[:3, :] = torch.randn(3, 4, generator=gen)
+            else:
+                q = torch.randn(4, generator=gen)
+                w, x, y, z = (q / q.norm()).tolist()
+                T = torch.eye(4)
+                T[:3, :3] = torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                                          [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+                T[:3, 3] = torch.randn(3, generator=gen) * 3.0
+            T = T.to(device)
+            a = ext.camera_centre(T)
+            b = torch.linalg.inv_ex(T)[0][:3, 3].contiguous()
+            same = same and bool((a.view(torch.int32) == b.view(torch.int32)).all())
+    _CENTRE_OK[idx] = same
+    if not same:
+        warnings.warn("gaussian_splatting_b200: gsr_camera_centre no longer reproduces torch.linalg.inv_ex bit for "
+                      "bit on this device; using torch's inverse for the camera centre", RuntimeWarning)
+    return same
+
+
 def _depth_key_params(near, far):
     """(base, bits): depth keys are float bits of z minus `base`; `bits` low bits are significant."""
     import math
@@ -169,11 +210,15 @@ class _ProjectGaussians(torch.autograd.Function):
             xyz_cam = transform_points_torch(xyz[N - tail:], camera_T_world) if 0 < tail < SMALL_BATCH else None
         else:
             xyz_cam = transform_points_torch(xyz, camera_T_world)
-        # camera centre for the SH view direction: same LU-based inverse as the reference's torch.inverse
-        # (splat_py/rasterize.py:91-93), through inv_ex so that no host sync is involved
+        # camera centre for the SH view direction = inverse(camera_T_world)[:3, 3] with the bits of the reference's
+        # torch.inverse (splat_py/rasterize.py:91-93): ONE native kernel that reproduces torch's LU arithmetic
+        # (verified per device, native_centre_ok), else torch's own inverse (inv_ex: no host sync)
         centre = None
         if sh is not None:
-            centre = torch.linalg.inv_ex(camera_T_world)[0][:3, 3].contiguous()
+            if native_centre_ok(xyz.device):
+                centre = ext.camera_centre(camera_T_world)
+            else:
+                centre = torch.linalg.inv_ex(camera_T_world)[0][:3, 3].contiguous()
         with _stage(state, "preprocess_fwd"):
             records, zkey, visible, scan = ext.fused_preprocess_forward(
                 xyz, xyz_cam, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, centre, H, W, near, far,
@@ -189,11 +234,13 @@ class _ProjectGaussians(torch.autograd.Function):
             ids_sorted, ranges, stream_rec, vis_idx, uv = ext.fused_bin(records, zkey, visible, scan, M, P, H, W, mh,
                                                                         depth_bits)
         state.N, state.M, state.P, state.H, state.W = xyz.shape[0], M, P, H, W
-        state.visible, state.vis_idx = visible, vis_idx.long()  # int64: index_copy_ needs it
-        state.vis_idx32 = vis_idx                                # int32 original, for the native ops
+        state.visible = visible
+        state.vis_idx = state.vis_idx32 = vis_idx                # int32 [M]: visible gaussians, ascending
+        # ids_sorted[p]: RANK among the visible gaussians of sorted pair p's gaussian (the gaussian is
+        # vis_idx[rank]) = its row in the compact gradient slab
         state.ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec
         state.scan = scan
-        carrier = torch.empty(9 * xyz.shape[0], dtype=xyz.dtype, device=xyz.device)
+        carrier = torch.empty(9 * M, dtype=xyz.dtype, device=xyz.device)
         ctx.state = state
         ctx.has_sh = sh is not None
         ctx.save_for_backward(xyz, quaternion, scale, opacity_flat, sh, camera_T_world, K, centre)
@@ -205,18 +252,18 @@ class _ProjectGaussians(torch.autograd.Function):
         st = ctx.state
         N = st.N
         if grad_carrier is None:
-            grad_carrier = torch.zeros(9 * N, dtype=xyz.dtype, device=xyz.device)
+            grad_carrier = torch.zeros(9 * st.M, dtype=xyz.dtype, device=xyz.device)
         slab = grad_carrier.contiguous()
-        # The gradient autograd hands us for the compact uv is the TOTAL (render contribution + anything the
-        # caller added upstream of uv); the kernel reads it directly, row = rank among the visible gaussians
-        # (from the forward's scan), instead of the slab's uv section.  Incoming gradients are never edited.
+        # The slab is COMPACT: row r belongs to the r-th visible gaussian (the kernel finds r in the forward's
+        # scan).  The gradient autograd hands us for the compact uv is the TOTAL (render contribution + anything
+        # the caller added upstream of uv) and is read in place of the slab's uv section; nothing is edited.
         guv = None
         if grad_uv is not None and st.M > 0:
             guv = grad_uv.contiguous()
         with _stage(st, "preprocess_bwd"):
             grads = native().fused_preprocess_backward(slab, xyz, quaternion, scale, opacity_flat, sh,
                                                        camera_T_world, K, centre, st.visible, st.grad_out,
-                                                       guv, st.scan if guv is not None else None)
+                                                       guv, st.scan, st.M)
         g_xyz, g_q, g_s, g_o, g_dc = grads[:5]
         g_sh = grads[5] if ctx.has_sh else None
         st.grad_flat = grads[-1]  # the one allocation all parameter gradients of this view are views of
@@ -239,11 +286,11 @@ class _CompositeTiles(torch.autograd.Function):
     def backward(ctx, grad_image):
         st = ctx.state
         with _stage(st, "render_bwd"):
-            slab = native().fused_render_backward(grad_image.contiguous(), st.N, st.stream_rec, st.ids_sorted,
+            slab = native().fused_render_backward(grad_image.contiguous(), st.M, st.stream_rec, st.ids_sorted,
                                                   st.ranges, st.background, st.n_per_pixel, st.w_per_pixel, st.masks)
-        N = st.N
-        grad_uv = slab[4 * N:6 * N].view(N, 2).index_select(0, st.vis_idx)
-        return grad_uv, slab, None, None
+        M = st.M
+        # the uv section of the compact slab IS the gradient of the compact uv: a view, no gather
+        return slab[4 * M:6 * M].view(M, 2), slab, None, None
 
 
 def rasterize(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist,

@@ -185,6 +185,11 @@ int gsr_render_depth(int N, const float* xyz_camera_frame, const float* uvs, con
  * count for every Gaussian; results are bit-identical to running the
  * reference's operator chain on the survivors.
  * ---------------------------------------------------------------------- */
+/* centre [3] <- inverse(camera_T_world)[:3, 3]: the camera centre in world coordinates that the SH view
+ * directions use (splat_py/rasterize.py:91-93 `torch.inverse(camera_T_world)`, src/precompute_sh.cu:149-151), with the
+ * bits torch's LU-based inverse produces for one 4x4 fp32 matrix (one tiny kernel instead of torch's 15). */
+int gsr_camera_centre(const float* camera_T_world, float* centre, void* stream);
+
 size_t gsr_preprocess_temp_bytes(int N);
 /* inputs: xyz [N,3], quaternion [N,4], scale [N,3], opacity_logit [N], rgb_dc [N,3],
  *         sh_rest [N,3,n_sh_rest] (n_sh_rest in {0,3,8,15}; may be NULL when 0),
@@ -227,9 +232,11 @@ int gsr_sort_pairs(int P, int n_tiles, int depth_bits, const uint64_t* keys_in, 
 int gsr_tile_ranges(int P, int n_tiles, int depth_bits, const uint64_t* keys_sorted, int32_t* tile_ranges,
                     void* stream);
 
-/* records_sorted[p] = records[ids_sorted[p]] (48-byte rows) */
+/* records_sorted[p] = records[ids_sorted[p]] (48-byte rows).  scan / ranks_sorted (both or neither): also
+ * ranks_sorted[p] = (scan[ids_sorted[p]] >> 32) - 1, the gaussian's rank among the visible ones = its row in
+ * compact per-gaussian gradient arrays (see gsr_preprocess_backward). */
 int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, float* records_sorted,
-                       void* stream);
+                       const uint64_t* scan, int32_t* ranks_sorted, void* stream);
 
 /* Keys-only variant of the four calls above: when tile bits + depth_bits + id bits fit in 64, the gaussian id
  * rides in the low id_bits of the key — (tile | depth | id) — and ONE cub::DeviceRadixSort::SortKeys over bits
@@ -244,22 +251,22 @@ int gsr_emit_keys(int N, const float* records, const uint32_t* depth_key, const 
 size_t gsr_sort_keys_temp_bytes(int P);
 int gsr_sort_keys(int P, int n_tiles, int depth_bits, int id_bits, const uint64_t* keys_in, uint64_t* keys_out,
                   void* temp, size_t temp_bytes, void* stream);
+/* ids_sorted[p] = the gaussian id of sorted pair p, or — scan != NULL — its rank among the visible gaussians */
 int gsr_gather_records_keys(int P, int id_bits, const uint64_t* keys_sorted, const float* records,
-                            float* records_sorted, int32_t* ids_sorted, void* stream);
+                            float* records_sorted, int32_t* ids_sorted, const uint64_t* scan, void* stream);
 
-/* backward of the fused per-Gaussian stage.  grad_rgb/grad_opacity/grad_uv/grad_conic are indexed by
- * ORIGINAL gaussian index (as accumulated by gsr_render_backward).  When grad_uv_compact is not NULL it is
- * the TOTAL gradient on the compact uv [M,2] that rasterize returned (render contribution + anything the
- * caller added upstream, what autograd hands to the projection node) and replaces grad_uv: the row of visible
- * gaussian i is (scan[i] >> 32) - 1, scan = the packed inclusive scan of gsr_preprocess_forward.  Writes dense
- * parameter gradients for all N gaussians (zeros for culled ones). */
+/* backward of the fused per-Gaussian stage.  grad_rgb [.,3] / grad_opacity [.] / grad_uv [.,2] / grad_conic [.,3]
+ * are the per-gaussian sums the render backward accumulated (grad_uv: plus anything the caller added upstream of
+ * the compact uv — the total gradient autograd hands to the projection node).  scan == NULL: N rows each, indexed
+ * by gaussian.  scan != NULL (the packed inclusive scan of gsr_preprocess_forward): COMPACT arrays of M rows,
+ * visible gaussian i at row (scan[i] >> 32) - 1, i.e. in the order of vis_idx / of the uv rasterize returns.
+ * Writes dense parameter gradients for all N gaussians (zeros for culled ones). */
 int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
                             const float* scale, const float* opacity_logit, const float* camera_T_world,
                             const float* K, const float* camera_centre, const uint8_t* visible, const float* grad_rgb,
                             const float* grad_opacity, const float* grad_uv, const float* grad_conic,
-                            const float* grad_uv_compact, const uint64_t* scan,
-                            float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
-                            float* g_rgb_dc, float* g_sh_rest, void* stream);
+                            const uint64_t* scan, float* g_xyz, float* g_quaternion, float* g_scale,
+                            float* g_opacity_logit, float* g_rgb_dc, float* g_sh_rest, void* stream);
 
 /* ---- optimizer step on the flat parameter buffer ----------------------------
  * Replaces torch.optim.Adam.step() as configured by splat_py/optimizer_manager.py:13-44 (one parameter group
