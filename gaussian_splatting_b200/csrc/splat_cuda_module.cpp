@@ -468,9 +468,8 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
     return std::make_tuple(records, zkey, visible, scan);
 }
 
-// (M, P known) -> row of the COMPACT per-gaussian gradient arrays each sorted pair accumulates into [P] i32
-//                 (= rank of its gaussian among the visible ones; the gaussian itself is vis_idx[rank]),
-//                 tile ranges [n_tiles+1] i32, sorted record stream [P,12], vis_idx [M] i32, uv [M,2]
+// (M, P known) -> sorted gaussian ids [P] i32, tile ranges [n_tiles+1] i32, sorted record stream [P,12],
+//                 vis_idx [M] i32, uv [M,2]
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_bin(
     torch::Tensor records, torch::Tensor zkey, torch::Tensor visible, torch::Tensor scan, int64_t M, int64_t P,
     int64_t H, int64_t W, double mh_dist, int64_t depth_bits) {
@@ -503,8 +502,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
                                  cur_stream()),
                  "gsr_tile_ranges");
         check_rc(gsr_gather_records_keys((int)P, id_bits, keys_b, F32PTR(records), F32PTR(stream_rec),
-                                         ids_sorted.data_ptr<int>(), (const uint64_t*)scan.data_ptr<int64_t>(),
-                                         cur_stream()),
+                                         ids_sorted.data_ptr<int>(), nullptr, cur_stream()),
                  "gsr_gather_records_keys");
     } else {
         torch::Tensor ids = torch::empty({Pa}, i32);
@@ -520,12 +518,9 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
                  "gsr_sort_pairs");
         check_rc(gsr_tile_ranges((int)P, n_tiles, (int)depth_bits, keys_b, ranges.data_ptr<int>(), cur_stream()),
                  "gsr_tile_ranges");
-        torch::Tensor ranks = torch::empty({Pa}, i32);
         check_rc(gsr_gather_records((int)P, (const uint32_t*)ids_sorted.data_ptr<int>(), F32PTR(records),
-                                    F32PTR(stream_rec), (const uint64_t*)scan.data_ptr<int64_t>(),
-                                    ranks.data_ptr<int>(), cur_stream()),
+                                    F32PTR(stream_rec), nullptr, nullptr, cur_stream()),
                  "gsr_gather_records");
-        ids_sorted = ranks;
     }
     return std::make_tuple(ids_sorted.narrow(0, 0, P), ranges, stream_rec, vis_idx, uv);
 }
@@ -551,9 +546,8 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_ren
     return std::make_tuple(image, n, w, masks);
 }
 
-// per-gaussian gradient slab, flat [9M]: rgb [M,3] | opacity [M] | uv [M,2] | conic [M,3], rows indexed by the
-// gaussian's RANK among the visible ones (ids_sorted holds that rank per pair); zero-filled, then accumulated into
-// by the render backward.  The uv section IS the gradient of the compact uv rasterize returned.
+// per-gaussian gradient slab, flat [9N]: rgb [N,3] | opacity [N] | uv [N,2] | conic [N,3], rows indexed by
+// gaussian; zero-filled, then accumulated into by the render backward
 torch::Tensor fused_render_backward(torch::Tensor grad_image, int64_t N, torch::Tensor stream_rec,
                                     torch::Tensor ids_sorted, torch::Tensor ranges, torch::Tensor background,
                                     torch::Tensor n, torch::Tensor w, torch::Tensor masks) {
@@ -576,8 +570,9 @@ torch::Tensor fused_render_backward(torch::Tensor grad_image, int64_t N, torch::
     return slab;
 }
 
-// grads of (xyz, quaternion, scale, opacity_logit, rgb_dc[, sh_rest]) from the compact slab [9M] (rows in vis_idx
-// order) and the total gradient on the compact uv [M,2] (None: the slab's own uv section)
+// grads of (xyz, quaternion, scale, opacity_logit, rgb_dc[, sh_rest]) from the slab [9N] (rows by gaussian).
+// grad_uv_compact [M,2] (optional): gradient on the compact uv, added to — or, with use_slab_uv false, replacing —
+// the slab's uv section.
 std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::Tensor xyz,
                                                      torch::Tensor quaternion, torch::Tensor scale,
                                                      torch::Tensor opacity_logit,
@@ -586,25 +581,28 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
                                                      c10::optional<torch::Tensor> camera_centre,
                                                      torch::Tensor visible,
                                                      c10::optional<torch::Tensor> out_flat,
-                                                     c10::optional<torch::Tensor> grad_uv_total,
-                                                     torch::Tensor scan, int64_t M) {
+                                                     c10::optional<torch::Tensor> grad_uv_compact,
+                                                     c10::optional<torch::Tensor> scan, bool use_slab_uv) {
     CHECK_VALID_INPUT(slab); CHECK_FLOAT_TENSOR(slab);
     const int64_t N = xyz.size(0);
-    TORCH_CHECK(slab.numel() == M * 9, "gradient slab must hold 9 floats per visible gaussian");
-    TORCH_CHECK(scan.numel() == N && scan.scalar_type() == torch::kInt64, "scan: the packed scan of the forward pass");
+    TORCH_CHECK(slab.numel() == N * 9, "gradient slab must hold 9 floats per gaussian");
     c10::cuda::CUDAGuard guard(xyz.device());
     auto opt = xyz.options();
     const float* g_rgb = slab.data_ptr<float>();
-    const float* g_opa = g_rgb + (size_t)M * 3;
-    const float* g_uv = g_opa + (size_t)M;
-    const float* g_conic = g_uv + (size_t)M * 2;
+    const float* g_opa = g_rgb + (size_t)N * 3;
+    const float* g_uv = use_slab_uv ? g_opa + (size_t)N : nullptr;
+    const float* g_conic = g_opa + (size_t)N * 3;
     const int n_rest = sh_rest.has_value() ? (int)sh_rest->size(2) : 0;
-    if (grad_uv_total.has_value() && grad_uv_total->numel() > 0) {
-        CHECK_VALID_INPUT((*grad_uv_total)); CHECK_FLOAT_TENSOR((*grad_uv_total));
-        TORCH_CHECK(grad_uv_total->numel() == 2 * M, "grad_uv_total must be Mx2");
-        g_uv = grad_uv_total->data_ptr<float>();
+    const float* g_uv_compact = nullptr;
+    const uint64_t* scan_ptr = nullptr;
+    if (grad_uv_compact.has_value() && grad_uv_compact->numel() > 0) {
+        CHECK_VALID_INPUT((*grad_uv_compact)); CHECK_FLOAT_TENSOR((*grad_uv_compact));
+        TORCH_CHECK(scan.has_value() && scan->numel() == N && scan->scalar_type() == torch::kInt64,
+                    "grad_uv_compact needs the packed scan of the forward pass");
+        TORCH_CHECK(grad_uv_compact->dim() == 2 && grad_uv_compact->size(1) == 2, "grad_uv_compact must be Mx2");
+        g_uv_compact = grad_uv_compact->data_ptr<float>();
+        scan_ptr = (const uint64_t*)scan->data_ptr<int64_t>();
     }
-    const uint64_t* scan_ptr = (const uint64_t*)scan.data_ptr<int64_t>();
     // All parameter gradients of a view live in ONE allocation, [xyz 3N | quaternion 4N | scale 3N |
     // opacity N | rgb 3N | sh 3*n_rest*N], every section starting on a 16-byte boundary (TMA bulk stores):
     // a trainer that sums gradients over views / ranks reduces that one buffer (view_parallel.py).
@@ -634,8 +632,8 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
     check_rc(gsr_preprocess_backward((int)N, n_rest, F32PTR(xyz), F32PTR(quaternion), F32PTR(scale),
                                      F32PTR(opacity_logit), F32PTR(camera_T_world), F32PTR(K),
                                      camera_centre.has_value() ? camera_centre->data_ptr<float>() : nullptr,
-                                     visible.data_ptr<uint8_t>(), g_rgb, g_opa, g_uv, g_conic, scan_ptr,
-                                     F32PTR(o_xyz),
+                                     visible.data_ptr<uint8_t>(), g_rgb, g_opa, g_uv, g_conic, g_uv_compact,
+                                     scan_ptr, F32PTR(o_xyz),
                                      F32PTR(o_q), F32PTR(o_s), F32PTR(o_o), F32PTR(o_dc),
                                      n_rest ? F32PTR(g_sh) : nullptr, cur_stream()),
              "gsr_preprocess_backward");

@@ -10,15 +10,17 @@ Implementation: two autograd nodes around the native fused kernels
     _ProjectGaussians   params -> uv [M,2], carrier          (gsr_preprocess_forward + binning)
     _CompositeTiles     uv, carrier -> image                  (gsr_render_forward)
 
-``carrier`` is an uninitialised [9M] tensor that only carries gradient: the render backward
-returns its per-Gaussian sums (rgb, opacity, uv, conic; one row per VISIBLE gaussian, in the order of
-the compact uv) as the carrier's gradient, and the per-Gaussian backward consumes them.  One host sync per forward (to size the pair buffers);
+``carrier`` is an uninitialised [9N] tensor that only carries gradient: the render backward
+returns its per-Gaussian sums (rgb, opacity, uv, conic) as the carrier's gradient, and the
+per-Gaussian backward consumes them.  One host sync per forward (to size the pair buffers);
 the reference path has ~25.
 
 ``use_sh_precompute=False`` (per-pixel view directions) is routed through the operator-by-operator
 path `rasterize_unfused`, which mirrors the reference's structure on this library's operators.
 """
 from __future__ import annotations
+
+import weakref
 
 import torch
 
@@ -165,12 +167,14 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
-                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "vis_idx32", "scan", "masks")
+                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "vis_idx32", "scan", "masks", "uv_ref", "uv_grad_emitted")
 
     def __init__(self, profile=None):
         self.profile = profile  # optional list: (stage name, start event, end event) per native call
         self.grad_flat = None   # set by the backward pass: flat buffer holding all parameter gradients
         self.grad_out = None    # optional caller-owned buffer (same layout) the backward writes them into
+        self.uv_ref = None      # weak reference to the uv tensor handed to the caller
+        self.uv_grad_emitted = False
 
 
 class _stage:
@@ -236,11 +240,9 @@ class _ProjectGaussians(torch.autograd.Function):
         state.N, state.M, state.P, state.H, state.W = xyz.shape[0], M, P, H, W
         state.visible = visible
         state.vis_idx = state.vis_idx32 = vis_idx                # int32 [M]: visible gaussians, ascending
-        # ids_sorted[p]: RANK among the visible gaussians of sorted pair p's gaussian (the gaussian is
-        # vis_idx[rank]) = its row in the compact gradient slab
         state.ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec
         state.scan = scan
-        carrier = torch.empty(9 * M, dtype=xyz.dtype, device=xyz.device)
+        carrier = torch.empty(9 * xyz.shape[0], dtype=xyz.dtype, device=xyz.device)
         ctx.state = state
         ctx.has_sh = sh is not None
         ctx.save_for_backward(xyz, quaternion, scale, opacity_flat, sh, camera_T_world, K, centre)
@@ -252,18 +254,21 @@ class _ProjectGaussians(torch.autograd.Function):
         st = ctx.state
         N = st.N
         if grad_carrier is None:
-            grad_carrier = torch.zeros(9 * st.M, dtype=xyz.dtype, device=xyz.device)
+            grad_carrier = torch.zeros(9 * N, dtype=xyz.dtype, device=xyz.device)
         slab = grad_carrier.contiguous()
-        # The slab is COMPACT: row r belongs to the r-th visible gaussian (the kernel finds r in the forward's
-        # scan).  The gradient autograd hands us for the compact uv is the TOTAL (render contribution + anything
-        # the caller added upstream of uv) and is read in place of the slab's uv section; nothing is edited.
+        # Gradient on the projected means: the render backward's sums sit in the slab's uv section (by gaussian).
+        # What autograd hands us for the COMPACT uv is either nothing / only what the caller added upstream of uv
+        # (the render node did not emit its part: added to the slab's section in the kernel, row = rank among the
+        # visible gaussians from the forward's scan), or the TOTAL (the render node did emit it because somebody
+        # watches uv.grad: it then replaces the slab's section).  Incoming gradients are never edited.
         guv = None
         if grad_uv is not None and st.M > 0:
             guv = grad_uv.contiguous()
         with _stage(st, "preprocess_bwd"):
             grads = native().fused_preprocess_backward(slab, xyz, quaternion, scale, opacity_flat, sh,
                                                        camera_T_world, K, centre, st.visible, st.grad_out,
-                                                       guv, st.scan, st.M)
+                                                       guv, st.scan if guv is not None else None,
+                                                       not st.uv_grad_emitted)
         g_xyz, g_q, g_s, g_o, g_dc = grads[:5]
         g_sh = grads[5] if ctx.has_sh else None
         st.grad_flat = grads[-1]  # the one allocation all parameter gradients of this view are views of
@@ -286,11 +291,20 @@ class _CompositeTiles(torch.autograd.Function):
     def backward(ctx, grad_image):
         st = ctx.state
         with _stage(st, "render_bwd"):
-            slab = native().fused_render_backward(grad_image.contiguous(), st.M, st.stream_rec, st.ids_sorted,
+            slab = native().fused_render_backward(grad_image.contiguous(), st.N, st.stream_rec, st.ids_sorted,
                                                   st.ranges, st.background, st.n_per_pixel, st.w_per_pixel, st.masks)
-        M = st.M
-        # the uv section of the compact slab IS the gradient of the compact uv: a view, no gather
-        return slab[4 * M:6 * M].view(M, 2), slab, None, None
+        # The render pass's gradient on the compact uv is a gather of the slab's uv section (28 us at 3M).  It
+        # reaches the per-gaussian backward through the slab anyway, so it is only materialised when it can be
+        # OBSERVED: the caller retained uv's gradient (the reference trainer does, splat_py/trainer.py:360) or
+        # hooked the tensor.
+        uv_t = st.uv_ref() if st.uv_ref is not None else None
+        watched = uv_t is None or uv_t.retains_grad or bool(uv_t._backward_hooks)
+        st.uv_grad_emitted = bool(watched)
+        if not watched:
+            return None, slab, None, None
+        N = st.N
+        grad_uv = slab[4 * N:6 * N].view(N, 2).index_select(0, st.vis_idx)
+        return grad_uv, slab, None, None
 
 
 def rasterize(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_mask_padding, mh_dist,
@@ -309,6 +323,7 @@ def rasterize(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_m
         gaussians.opacity.contiguous(), gaussians.rgb.contiguous(),
         None if gaussians.sh is None else gaussians.sh.contiguous(),
         camera_T_world.contiguous(), camera.K.contiguous(), state, cfg)
+    state.uv_ref = weakref.ref(uv)
     image = _CompositeTiles.apply(uv, carrier, background_rgb.contiguous(), state)
     culling_mask = state.visible == 0
     if return_state:

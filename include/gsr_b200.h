@@ -255,18 +255,18 @@ int gsr_sort_keys(int P, int n_tiles, int depth_bits, int id_bits, const uint64_
 int gsr_gather_records_keys(int P, int id_bits, const uint64_t* keys_sorted, const float* records,
                             float* records_sorted, int32_t* ids_sorted, const uint64_t* scan, void* stream);
 
-/* backward of the fused per-Gaussian stage.  grad_rgb [.,3] / grad_opacity [.] / grad_uv [.,2] / grad_conic [.,3]
- * are the per-gaussian sums the render backward accumulated (grad_uv: plus anything the caller added upstream of
- * the compact uv — the total gradient autograd hands to the projection node).  scan == NULL: N rows each, indexed
- * by gaussian.  scan != NULL (the packed inclusive scan of gsr_preprocess_forward): COMPACT arrays of M rows,
- * visible gaussian i at row (scan[i] >> 32) - 1, i.e. in the order of vis_idx / of the uv rasterize returns.
+/* backward of the fused per-Gaussian stage.  grad_rgb [N,3] / grad_opacity [N] / grad_uv [N,2] / grad_conic [N,3]
+ * are the per-gaussian sums the render backward accumulated (indexed by gaussian).  The gradient on a projected
+ * mean is grad_uv[i] (skipped when grad_uv is NULL) PLUS grad_uv_compact[(scan[i] >> 32) - 1] (skipped when NULL):
+ * grad_uv_compact [M,2] is a gradient on the compact uv rasterize returned, in its order (scan = the packed
+ * inclusive scan of gsr_preprocess_forward) — what a caller added upstream of uv, or the total autograd hands over.
  * Writes dense parameter gradients for all N gaussians (zeros for culled ones). */
 int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
                             const float* scale, const float* opacity_logit, const float* camera_T_world,
                             const float* K, const float* camera_centre, const uint8_t* visible, const float* grad_rgb,
                             const float* grad_opacity, const float* grad_uv, const float* grad_conic,
-                            const uint64_t* scan, float* g_xyz, float* g_quaternion, float* g_scale,
-                            float* g_opacity_logit, float* g_rgb_dc, float* g_sh_rest, void* stream);
+                            const float* grad_uv_compact, const uint64_t* scan, float* g_xyz, float* g_quaternion,
+                            float* g_scale, float* g_opacity_logit, float* g_rgb_dc, float* g_sh_rest, void* stream);
 
 /* ---- optimizer step on the flat parameter buffer ----------------------------
  * Replaces torch.optim.Adam.step() as configured by splat_py/optimizer_manager.py:13-44 (one parameter group

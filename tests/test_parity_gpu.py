@@ -535,19 +535,41 @@ def test_against_cpu_oracle(nG, res, sig, shd):
 # ------------------------------------------------------------------------------------------------
 def test_upstream_gradient_on_uv():
     """A loss that also depends on the returned uv: the fused backward must add the upstream uv gradient to the
-    render's own (and must not when nothing is added — same result as the operator-by-operator chain)."""
+    render's own — whether or not the render node materialises its compact uv gradient (it does only when uv.grad
+    is observable: retain_grad() or a hook) — same result as the operator-by-operator chain, and uv.grad itself
+    must be the chain's."""
     sc = scenes.np_scene(4000, "tiny", sh_degree=0, seed=5, sigma_px=(2.0, 0.5, 0.5, 8.0))
     G = to_t(synth.make_upstream_grad("tiny").numpy())
     cam = Camera(sc["W"], sc["H"], to_t(sc["K"]))
     bg = torch.full((3,), 0.5, device=dev())
-    grads = {}
-    for name, fn in (("fused", rasterize), ("unfused", rasterize_unfused)):
+    grads, uv_grads, hooked = {}, {}, []
+    for name, fn, watch in (("fused", rasterize, None), ("fused-retain", rasterize, "retain"),
+                            ("fused-hook", rasterize, "hook"), ("unfused", rasterize_unfused, "retain")):
         g = gaussians_from(sc)
         image, _, uv = fn(g, to_t(sc["T"]), cam, 0.3, 500.0, 100, 3.0, True, bg)
+        if watch == "retain":
+            uv.retain_grad()
+        elif watch == "hook":
+            uv.register_hook(lambda gr: hooked.append(gr.clone()))
         ((image * G).sum() + 1e-6 * (uv * uv).sum()).backward()
         grads[name] = (g.xyz.grad.clone(), g.scale.grad.clone())
-    for a, b in zip(grads["fused"], grads["unfused"]):
-        assert rel(a, b) < REL_TOL, rel(a, b)
+        if watch == "retain":
+            uv_grads[name] = uv.grad.clone()
+    for name in ("fused", "fused-retain", "fused-hook"):
+        for a, b in zip(grads[name], grads["unfused"]):
+            assert rel(a, b) < REL_TOL, (name, rel(a, b))
+    assert rel(uv_grads["fused-retain"], uv_grads["unfused"]) < REL_TOL
+    assert len(hooked) == 1 and rel(hooked[0], uv_grads["unfused"]) < REL_TOL
+    # only the render's gradient, observed: uv.grad without any upstream term
+    g = gaussians_from(sc)
+    image, _, uv = rasterize(g, to_t(sc["T"]), cam, 0.3, 500.0, 100, 3.0, True, bg)
+    uv.retain_grad()
+    (image * G).sum().backward()
+    g2 = gaussians_from(sc)
+    image2, _, uv2 = rasterize(g2, to_t(sc["T"]), cam, 0.3, 500.0, 100, 3.0, True, bg)
+    (image2 * G).sum().backward()
+    assert uv2.grad is None and float(uv.grad.abs().max()) > 0
+    assert rel(g2.xyz.grad, g.xyz.grad) < 1e-5 and rel(g2.scale.grad, g.scale.grad) < 1e-5
 
 
 def test_everything_culled_gives_background():
@@ -638,7 +660,7 @@ def test_full_size_properties():
     ranges = st.ranges.long()
     assert ranges[0] == 0 and ranges[-1] == st.P and bool((ranges[1:] >= ranges[:-1]).all())
     z = (T[2, :3] @ g.xyz.detach().T + T[2, 3])
-    zs = z[st.vis_idx.long()[st.ids_sorted.long()]]  # ids_sorted: rank among the visible gaussians
+    zs = z[st.ids_sorted.long()]
     tile_of = torch.bucketize(torch.arange(st.P, device=d), ranges[1:], right=True)
     same = tile_of[1:] == tile_of[:-1]
     assert bool((zs[1:][same] >= zs[:-1][same] - 1e-4).all())

@@ -78,7 +78,7 @@ def write_points(path, xyz, rgb_u8):
             f.write(struct.pack("<Q3d3BdQ", i, *p, *[int(v) for v in c], 0.5, 0))  # empty track
 
 
-def ground_truth(n, seed):
+def ground_truth(n, seed, scale_lo=0.015, scale_hi=0.04):
     rng = np.random.default_rng(seed)
     shell = rng.choice([0.6, 1.0, 1.5], size=n, p=[0.2, 0.4, 0.4])
     d = rng.normal(size=(n, 3))
@@ -87,7 +87,7 @@ def ground_truth(n, seed):
     xyz[:, 2] *= 0.6
     # colour varies smoothly with position so that a sparse subsample carries useful initial colours
     rgb = 0.5 + 0.45 * np.sin(xyz @ rng.normal(scale=2.5, size=(3, 3)) + rng.uniform(0, 6.28, size=3))
-    scale = np.log(rng.uniform(0.015, 0.04, size=(n, 3)))
+    scale = np.log(rng.uniform(scale_lo, scale_hi, size=(n, 3)))
     quat = rng.normal(size=(n, 4))
     opacity = rng.uniform(1.0, 4.0, size=(n, 1))  # logit
     return [a.astype(np.float32) for a in (xyz, rgb, scale, quat, opacity)]
@@ -103,6 +103,8 @@ def main():
     ap.add_argument("--height", type=int, default=416)
     ap.add_argument("--focal", type=float, default=560.0)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--scale-lo", type=float, default=0.015, help="ground-truth gaussian extent (world units), lower bound")
+    ap.add_argument("--scale-hi", type=float, default=0.04)
     a = ap.parse_args()
 
     import cv2
@@ -112,7 +114,7 @@ def main():
     from gaussian_splatting_b200.structs import Camera, Gaussians
 
     dev = torch.device("cuda:0")
-    xyz, rgb, scale, quat, opacity = ground_truth(a.gaussians, a.seed)
+    xyz, rgb, scale, quat, opacity = ground_truth(a.gaussians, a.seed, a.scale_lo, a.scale_hi)
     g = Gaussians(xyz=torch.tensor(xyz, device=dev), rgb=torch.tensor(rgb / 0.28209479177387814, device=dev),
                   opacity=torch.tensor(opacity, device=dev), scale=torch.tensor(scale, device=dev),
                   quaternion=torch.tensor(quat, device=dev))

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--iters", type=int, default=7000)
     ap.add_argument("--max-gaussians", type=int, default=400000)
+    ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args()
 
     import torch
@@ -70,7 +71,7 @@ def main():
                          max_gaussians=a.max_gaussians, save_debug_image_interval=10 ** 9, print_interval=500,
                          checkpoint_interval=10 ** 9, **sched)
 
-    torch.manual_seed(0)
+    torch.manual_seed(a.seed)
     data = ColmapData(config.dataset_path, torch.device("cuda"), downsample_factor=config.downsample_factor, config=config)
     gaussians = data.create_gaussians()
     for name in ("xyz", "quaternion", "scale", "opacity", "rgb"):
@@ -86,7 +87,7 @@ def main():
 
     psnr, ssim = trainer.compute_test_psnr()
     line = {
-        "impl": a.impl, "iters": a.iters, "train_seconds": round(seconds, 2),
+        "impl": a.impl, "iters": a.iters, "seed": a.seed, "train_seconds": round(seconds, 2),
         "iters_per_second": round(a.iters / seconds, 2),
         "final_test_psnr": round(float(psnr.mean()), 3), "final_test_ssim": round(float(ssim.mean()), 4),
         "max_test_psnr": round(max(trainer.metrics.test_psnr + [float(psnr.mean())]), 3),
