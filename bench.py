@@ -42,8 +42,8 @@ N_GAUSS = 3_000_000
 RES = "1080p"
 SH_DEGREE = 3
 N_POSES = 8
-MY_KERNELS = ["k_preprocess_fwd", "k_emit_pairs_fused", "k_tile_ranges", "k_gather_records", "k_render_fwd",
-              "k_render_bwd", "k_preprocess_bwd"]
+MY_KERNELS = ["k_camera_centre", "k_preprocess_fwd", "k_emit_pairs_fused", "k_tile_ranges", "k_gather_records_keys",
+              "k_render_fwd", "k_render_bwd", "k_preprocess_bwd"]
 
 
 def log(msg):
