@@ -24,7 +24,7 @@ constexpr int BIN_THREADS = 256;
 __device__ __forceinline__ int walk_tiles(const Obb& o, float u, float v, int ntx, int nty,
                                           uint32_t zkey, uint32_t id, uint64_t* __restrict__ keys,
                                           uint32_t* __restrict__ ids, int64_t base, int depth_bits = 32,
-                                          int id_bits = 0) {
+                                          int id_bits = 0, int64_t cap = INT64_MAX) {
     int x0, x1, y0, y1;
     tile_window(u, v, o.radius_tiles, ntx, nty, x0, x1, y0, y1);
     int n = 0;
@@ -35,7 +35,7 @@ __device__ __forceinline__ int walk_tiles(const Obb& o, float u, float v, int nt
             const float top = __fmul_rn(__int2float_rn(ty), 16.0f);
             const float bottom = __fmul_rn(__int2float_rn(ty + 1), 16.0f);
             if (obb_hits_tile(o, left, right, top, bottom)) {
-                if (keys) {
+                if (keys && base + n < cap) {  // cap: capacity of a speculatively sized pair buffer
                     const uint32_t tile = (uint32_t)(ty * ntx + tx);
                     const uint64_t k = ((uint64_t)tile << depth_bits) | zkey;
                     if (id_bits > 0) {
@@ -85,8 +85,18 @@ __global__ void __launch_bounds__(BIN_THREADS)
                        const uint32_t* __restrict__ zkey, const uint8_t* __restrict__ visible,
                        const uint64_t* __restrict__ scan, int ntx, int nty, float mh, int depth_bits,
                        int id_bits, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
-                       int32_t* __restrict__ vis_idx, float* __restrict__ uv_compact) {
+                       int32_t* __restrict__ vis_idx, float* __restrict__ uv_compact, int64_t cap) {
     const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
+    if (cap > 0) {
+        // Speculatively sized buffers (the host has not read P yet): positions [P, cap) get the all-ones key, which
+        // sorts behind every real pair (tile field >= n_tiles) and is ignored by the range / gather kernels
+        const int64_t P = (int64_t)(scan[N - 1] & 0xffffffffu);
+        for (int64_t p = P + (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x; p < cap;
+             p += (int64_t)gridDim.x * BIN_THREADS) {
+            keys[p] = ~0ull;
+            if (ids != nullptr) ids[p] = 0u;
+        }
+    }
     if (i >= N) return;
     if (!visible[i]) return;
     const uint64_t incl = scan[i];
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(BIN_THREADS)
     const float* r = records + (size_t)i * REC;
     compute_obb(u, v, r[R_A], __fmul_rn(r[R_B2], 0.5f), r[R_C], mh, o);
     walk_tiles(o, u, v, ntx, nty, zkey[i], (uint32_t)i, keys, ids, (int64_t)(prev & 0xffffffffu), depth_bits,
-               id_bits);
+               id_bits, cap > 0 ? cap : INT64_MAX);
 }
 
 // tile_ranges[t] = first sorted position whose tile id >= t  (ranges[n_tiles] = P).
@@ -114,13 +124,15 @@ __global__ void __launch_bounds__(BIN_THREADS)
     __shared__ int32_t s_tile[BIN_THREADS + 1];
     const int p0 = blockIdx.x * BIN_THREADS;
     const int p = p0 + threadIdx.x;
-    if (p < P) s_tile[threadIdx.x + 1] = (int32_t)(keys[p] >> depth_bits);
-    if (threadIdx.x == 0) s_tile[0] = (p0 > 0) ? (int32_t)(keys[p0 - 1] >> depth_bits) : -1;
+    // padding keys (all ones, speculatively sized buffers) carry a tile field >= n_tiles: clamp it, so that the
+    // first padding position closes every remaining range and the others close nothing
+    if (p < P) s_tile[threadIdx.x + 1] = (int32_t)min((uint64_t)n_tiles, keys[p] >> depth_bits);
+    if (threadIdx.x == 0) s_tile[0] = (p0 > 0) ? (int32_t)min((uint64_t)n_tiles, keys[p0 - 1] >> depth_bits) : -1;
     __syncthreads();
     if (p >= P) return;
     const int cur = s_tile[threadIdx.x + 1];
     const int prev = s_tile[threadIdx.x];
-    for (int t = prev + 1; t <= cur; ++t) ranges[t] = p;
+    for (int t = prev + 1; t <= cur; ++t) ranges[t] = p;  // cur <= n_tiles: ranges has n_tiles + 1 entries
     if (p == P - 1)
         for (int t = cur + 1; t <= n_tiles; ++t) ranges[t] = P;
 }
@@ -158,7 +170,9 @@ __global__ void __launch_bounds__(BIN_THREADS)
     const int64_t t = (int64_t)blockIdx.x * BIN_THREADS + threadIdx.x;
     if (t >= (int64_t)P * 3) return;
     const int p = (int)(t / 3), lane = (int)(t % 3);
-    const uint32_t id = (uint32_t)(keys[p] & id_mask);
+    const uint64_t key = keys[p];
+    if (key == ~0ull) return;  // padding of a speculatively sized buffer
+    const uint32_t id = (uint32_t)(key & id_mask);
     if (lane == 0) ids_out[p] = (scan != nullptr) ? (int32_t)(scan[id] >> 32) - 1 : (int32_t)id;
     out[t] = __ldg(rec + (size_t)id * 3 + lane);
 }
@@ -179,10 +193,12 @@ __global__ void __launch_bounds__(BIN_THREADS)
     o[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
 }
 
+// tile field width: 2^bits > n_tiles (strictly), so that the all-ones tile id never names a real tile — it is the
+// padding key of speculatively sized pair buffers and must sort behind every real pair
 static inline int sort_end_bit(int n_tiles, int depth_bits) {
-    int bits = 0;
-    while ((1 << bits) < n_tiles) ++bits;
-    return depth_bits + (bits > 0 ? bits : 1);
+    int bits = 1;
+    while ((1 << bits) <= n_tiles) ++bits;
+    return depth_bits + bits;
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -273,11 +289,12 @@ int gsr_binning_emit_sort(int N, int P, const float* uvs, const float* xyz_cam, 
 
 int gsr_emit_pairs(int N, const float* records, const uint32_t* depth_key,
                    const uint8_t* visible, const uint64_t* scan, int ntx, int nty, float mh, int depth_bits,
-                   uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, void* stream) {
+                   uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, int64_t capacity,
+                   void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
     k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, depth_bits, 0, keys,
-                                     ids, vis_idx, uv_compact);
+                                     ids, vis_idx, uv_compact, capacity);
     return (int)cudaGetLastError();
 }
 
@@ -290,12 +307,12 @@ int gsr_packed_id_bits(int N, int n_tiles, int depth_bits) {
 
 int gsr_emit_keys(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
                   const uint64_t* scan, int ntx, int nty, float mh, int depth_bits, int id_bits, uint64_t* keys,
-                  int32_t* vis_idx, float* uv_compact, void* stream) {
+                  int32_t* vis_idx, float* uv_compact, int64_t capacity, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
     if (id_bits < 1 || id_bits != gsr_packed_id_bits(N, ntx * nty, depth_bits)) return GSR_ERR_BAD_ARG;
     k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, depth_bits, id_bits, keys,
-                                     nullptr, vis_idx, uv_compact);
+                                     nullptr, vis_idx, uv_compact, capacity);
     return (int)cudaGetLastError();
 }
 

@@ -470,9 +470,12 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
 
 // (M, P known) -> sorted gaussian ids [P] i32, tile ranges [n_tiles+1] i32, sorted record stream [P,12],
 //                 vis_idx [M] i32, uv [M,2]
+// speculative = true: M and P are CAPACITIES (the host has not read the real counts yet): buffers are sized by
+// them, the pair buffer is padded behind the real pairs (gsr_emit_*'s `capacity`), and every tensor is returned at
+// full capacity — the caller narrows them once it knows M and P, and redoes the call if P exceeded the capacity.
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_bin(
     torch::Tensor records, torch::Tensor zkey, torch::Tensor visible, torch::Tensor scan, int64_t M, int64_t P,
-    int64_t H, int64_t W, double mh_dist, int64_t depth_bits) {
+    int64_t H, int64_t W, double mh_dist, int64_t depth_bits, bool speculative) {
     const int N = records.size(0);
     const int ntx = (W + 15) / 16, nty = (H + 15) / 16, n_tiles = ntx * nty;
     c10::cuda::CUDAGuard guard(records.device());
@@ -491,7 +494,8 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
     if (id_bits > 0) {  // (tile | depth | id) keys, keys-only radix sort
         check_rc(gsr_emit_keys(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(), visible.data_ptr<uint8_t>(),
                                (const uint64_t*)scan.data_ptr<int64_t>(), ntx, nty, (float)mh_dist, (int)depth_bits,
-                               id_bits, keys_a, vis_idx.data_ptr<int>(), F32PTR(uv), cur_stream()),
+                               id_bits, keys_a, vis_idx.data_ptr<int>(), F32PTR(uv), speculative ? P : 0,
+                               cur_stream()),
                  "gsr_emit_keys");
         const size_t sb = gsr_sort_keys_temp_bytes((int)P);
         torch::Tensor temp = torch::empty({(int64_t)sb}, opt.dtype(torch::kUInt8));
@@ -509,7 +513,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
         check_rc(gsr_emit_pairs(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(),
                                 visible.data_ptr<uint8_t>(), (const uint64_t*)scan.data_ptr<int64_t>(), ntx, nty,
                                 (float)mh_dist, (int)depth_bits, keys_a, (uint32_t*)ids.data_ptr<int>(),
-                                vis_idx.data_ptr<int>(), F32PTR(uv), cur_stream()),
+                                vis_idx.data_ptr<int>(), F32PTR(uv), speculative ? P : 0, cur_stream()),
                  "gsr_emit_pairs");
         const size_t sb = gsr_sort_pairs_temp_bytes((int)P);
         torch::Tensor temp = torch::empty({(int64_t)sb}, opt.dtype(torch::kUInt8));

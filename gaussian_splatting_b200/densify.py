@@ -257,12 +257,21 @@ class AdaptiveDensityControl:
         ... on the reference's schedule: adc.adaptive_density_control(i); adc.reset_opacity(); adc.add_sh_band()
     """
 
-    def __init__(self, gaussians, optimizer, stats: DensificationStats, config):
+    def __init__(self, gaussians, optimizer, stats: DensificationStats, config, alloc_flat=None):
+        """alloc_flat(n_floats) -> fp32 buffer: where a re-laid-out parameter buffer is to live (e.g. symmetric
+        memory for the sharded optimizer); default: an ordinary allocation."""
         self.gaussians, self.optimizer, self.stats, self.config = gaussians, optimizer, stats, config
+        self.alloc_flat = alloc_flat
 
     def adaptive_density_control(self, iteration: int):
+        from .flat_adam import section_ends
+
         plan = plan_adaptive_density_control(self.gaussians, self.stats, self.config, iteration)
-        apply_plan(plan, self.gaussians, self.optimizer, self.stats)
+        out_flat = None
+        if self.alloc_flat is not None and not plan.is_identity():
+            n_rest = 0 if self.gaussians.sh is None else int(self.gaussians.sh.shape[2])
+            out_flat = self.alloc_flat(section_ends(plan.n_out, n_rest)[-1])
+        apply_plan(plan, self.gaussians, self.optimizer, self.stats, out_flat=out_flat)
         return plan.info
 
     def reset_opacity(self):
@@ -298,8 +307,13 @@ class AdaptiveDensityControl:
             return False
         n = g.xyz.shape[0]
         ends_new = section_ends(n, new)
-        flat_new = torch.zeros(ends_new[-1], dtype=torch.float32, device=g.xyz.device)
-        m_new, v_new = torch.zeros_like(flat_new), torch.zeros_like(flat_new)
+        if self.alloc_flat is not None:
+            flat_new = self.alloc_flat(ends_new[-1])
+            flat_new.zero_()
+        else:
+            flat_new = torch.zeros(ends_new[-1], dtype=torch.float32, device=g.xyz.device)
+        m_new = torch.zeros(ends_new[-1], dtype=torch.float32, device=g.xyz.device)
+        v_new = torch.zeros_like(m_new)
         keep = opt.ends[4]  # xyz .. rgb sections are laid out identically (their ends do not depend on the sh width)
         flat_new[:keep].copy_(opt.p[:keep])
         m_new[:keep].copy_(opt.m[:keep])

@@ -104,6 +104,7 @@ class ShardedFlatAdam:
         import torch.distributed._symmetric_memory as symm_mem
 
         group = group if group is not None else dist.group.WORLD
+        self.group = group
         self.hp = symm_mem.rendezvous(params_flat, group)
         self.hg = symm_mem.rendezvous(grads_flat, group)
         self.rank, self.world = self.hp.rank, self.hp.world_size
@@ -118,6 +119,29 @@ class ShardedFlatAdam:
         self.v = torch.zeros_like(self.m)
         self.param_ptrs = [int(x) for x in self.hp.buffer_ptrs]
         self.grad_ptrs = [int(x) for x in self.hg.buffer_ptrs]
+
+    def full_state(self):
+        """(m, v) of the WHOLE flat buffer on every rank (all-gather of the shards): what a re-layout of the
+        parameter buffer (densification, a new SH band) needs before the state is sharded again."""
+        import torch.distributed as dist
+
+        n = self.p.numel()
+        per = ((n // 4 + self.world - 1) // self.world) * 4
+        out = []
+        for shard in (self.m, self.v):
+            padded = torch.zeros(per, dtype=torch.float32, device=shard.device)
+            padded[:shard.numel()].copy_(shard)
+            full = torch.empty(per * self.world, dtype=torch.float32, device=shard.device)
+            dist.all_gather_into_tensor(full, padded, group=self.group)
+            out.append(full[:n].contiguous())
+        return out[0], out[1]
+
+    def load_full_state(self, m_full: torch.Tensor, v_full: torch.Tensor, t: int) -> None:
+        """Keep this rank's range of a full (m, v) pair (after a re-layout) and the step count."""
+        assert m_full.numel() == self.p.numel() == v_full.numel()
+        self.m.copy_(m_full[self.lo:self.hi])
+        self.v.copy_(v_full[self.lo:self.hi])
+        self.t = int(t)
 
     def step(self) -> None:
         self.t += 1

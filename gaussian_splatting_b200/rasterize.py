@@ -10,6 +10,9 @@ Implementation: two autograd nodes around the native fused kernels
     _ProjectGaussians   params -> uv [M,2], carrier          (gsr_preprocess_forward + binning)
     _CompositeTiles     uv, carrier -> image                  (gsr_render_forward)
 
+(The tile renderer's forward kernel is enqueued by the projection node, right behind the binning and BEFORE the
+host reads the pair count; `_CompositeTiles` only ties its image into the graph.)
+
 ``carrier`` is an uninitialised [9N] tensor that only carries gradient: the render backward
 returns its per-Gaussian sums (rgb, opacity, uv, conic) as the carrier's gradient, and the
 per-Gaussian backward consumes them.  One host sync per forward (to size the pair buffers);
@@ -104,6 +107,39 @@ def in_kernel_transform_ok(device, n: int = 70_000, seed: int = 1234) -> bool:
     return same
 
 
+# ---- speculative sizing of the pair buffers (see _ProjectGaussians.forward) -----------------------------------------
+SPECULATIVE_BINNING = os.environ.get("GSR_EAGER_COUNTS", "0") != "1"
+_PAIR_HISTORY = {}   # (device index, N, H, W) -> pair counts of the most recent views
+_PINNED = {}         # device index -> [pinned int64 ring, next slot]
+PAIR_HEADROOM = 1.04  # capacity = max(recent P) * headroom + 64 Ki pairs
+
+
+def _pair_capacity(key):
+    hist = _PAIR_HISTORY.get(key)
+    if not hist:
+        return None
+    cap = int(max(hist) * PAIR_HEADROOM) + 65536
+    return min((cap + 127) // 128 * 128, 2**31 - 128)
+
+
+def _note_pairs(key, P):
+    hist = _PAIR_HISTORY.setdefault(key, [])
+    hist.append(int(P))
+    del hist[:-8]
+    if len(_PAIR_HISTORY) > 64:  # scenes come and go (densification changes N): keep the table small
+        for k in list(_PAIR_HISTORY)[:-32]:
+            del _PAIR_HISTORY[k]
+
+
+def _pinned_slot(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ring = _PINNED.get(idx)
+    if ring is None:
+        ring = _PINNED[idx] = [torch.empty(16, dtype=torch.int64).pin_memory(), 0]
+    ring[1] = (ring[1] + 1) % 16
+    return ring[0][ring[1]:ring[1] + 1]
+
+
 _CENTRE_OK = {}  # device index -> bool: does gsr_camera_centre reproduce torch's inverse on this device?
 
 
@@ -167,7 +203,7 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
-                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "vis_idx32", "scan", "masks", "uv_ref", "uv_grad_emitted")
+                 "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "vis_idx32", "scan", "masks", "uv_ref", "uv_grad_emitted", "image", "speculation_overflowed")
 
     def __init__(self, profile=None):
         self.profile = profile  # optional list: (stage name, start event, end event) per native call
@@ -175,6 +211,9 @@ class _ViewState:
         self.grad_out = None    # optional caller-owned buffer (same layout) the backward writes them into
         self.uv_ref = None      # weak reference to the uv tensor handed to the caller
         self.uv_grad_emitted = False
+        self.background = None  # set by rasterize() before the projection node runs (it pre-launches the renderer)
+        self.image = None
+        self.speculation_overflowed = False
 
 
 class _stage:
@@ -227,16 +266,55 @@ class _ProjectGaussians(torch.autograd.Function):
             records, zkey, visible, scan = ext.fused_preprocess_forward(
                 xyz, xyz_cam, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, centre, H, W, near, far,
                 pad, mh, depth_base)
-        total = int(scan[-1].item()) if xyz.shape[0] > 0 else 0  # the one host sync
-        M, P = total >> 32, total & 0xFFFFFFFF
-        # M and P share one u64 scan (M<<32 | P) and the native entry points index pairs with int32: a scene
-        # with >= 2^31 (gaussian, tile) pairs must fail loudly, not wrap into an empty render
-        if M > N or P >= 2**31:
-            raise RuntimeError(f"rasterize: {P} (gaussian, tile) pairs / {M} visible of {N} gaussians exceed the "
-                               "int32 pair index of the native path (P must be < 2^31)")
-        with _stage(state, "bin_sort_gather"):
-            ids_sorted, ranges, stream_rec, vis_idx, uv = ext.fused_bin(records, zkey, visible, scan, M, P, H, W, mh,
-                                                                        depth_bits)
+        record_masks = USE_CONTRIBUTION_MASKS and any(ctx.needs_input_grad[:6])  # a backward pass can follow
+        background = state.background
+
+        def counts(total):
+            M_, P_ = total >> 32, total & 0xFFFFFFFF
+            # M and P share one u64 scan (M<<32 | P) and the native entry points index pairs with int32: a scene
+            # with >= 2^31 (gaussian, tile) pairs must fail loudly, not wrap into an empty render
+            if M_ > N or P_ >= 2**31:
+                raise RuntimeError(f"rasterize: {P_} (gaussian, tile) pairs / {M_} visible of {N} gaussians exceed "
+                                   "the int32 pair index of the native path (P must be < 2^31)")
+            return M_, P_
+
+        def bin_and_render(M_, P_, speculative):
+            with _stage(state, "bin_sort_gather"):
+                binned = ext.fused_bin(records, zkey, visible, scan, M_, P_, H, W, mh, depth_bits, speculative)
+            with _stage(state, "render_fwd"):
+                rendered = ext.fused_render_forward(binned[2], binned[1], background, H, W, P_, record_masks)
+            return binned, rendered
+
+        # The host needs M and P (the shape of the returned uv; the size of the pair buffers).  Reading them right
+        # here stalls the GPU for a launch round trip (35 us resident, ~100 us when the step's host->device copies
+        # share the queue).  Instead the pair buffers are sized from the pair counts of the recent views of this
+        # (N, H, W) plus headroom, binning AND the tile renderer are enqueued, and only then the counts — copied to
+        # pinned memory right behind the scan — are read: by then they are long there.  Padding behind the real
+        # pairs sorts to the end and is ignored (gsr_emit_*'s capacity).  If a view overflows the guess, the two
+        # stages run again with the exact sizes (and the guess grows); the first view of a kind reads eagerly.
+        key = (xyz.device.index, N, H, W)
+        cap = _pair_capacity(key) if (SPECULATIVE_BINNING and N > 0) else None
+        if cap is None:
+            total = int(scan[-1].item()) if N > 0 else 0
+            M, P = counts(total)
+            binned, rendered = bin_and_render(M, P, False)
+        else:
+            slot = _pinned_slot(xyz.device)
+            slot.copy_(scan[-1:], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record()
+            binned, rendered = bin_and_render(N, cap, True)
+            ready.synchronize()
+            M, P = counts(int(slot.item()))
+            if P > cap:  # the guess was too small: nothing usable was produced, run the two stages again
+                binned, rendered = bin_and_render(M, P, False)
+                state.speculation_overflowed = True
+            else:
+                ids_c, ranges_c, stream_c, vis_c, uv_c = binned
+                binned = (ids_c.narrow(0, 0, P), ranges_c, stream_c, vis_c.narrow(0, 0, M), uv_c.narrow(0, 0, M))
+        _note_pairs(key, P)
+        ids_sorted, ranges, stream_rec, vis_idx, uv = binned
+        state.image, state.n_per_pixel, state.w_per_pixel, state.masks = rendered
         state.N, state.M, state.P, state.H, state.W = xyz.shape[0], M, P, H, W
         state.visible = visible
         state.vis_idx = state.vis_idx32 = vis_idx                # int32 [M]: visible gaussians, ascending
@@ -278,12 +356,9 @@ class _ProjectGaussians(torch.autograd.Function):
 class _CompositeTiles(torch.autograd.Function):
     @staticmethod
     def forward(ctx, uv, carrier, background_rgb, state):
-        with _stage(state, "render_fwd"):
-            # contribution masks are recorded only when a backward pass can follow
-            image, n_pp, w_pp, masks = native().fused_render_forward(
-                state.stream_rec, state.ranges, background_rgb, state.H, state.W, state.P,
-                USE_CONTRIBUTION_MASKS and any(ctx.needs_input_grad[:2]))
-        state.n_per_pixel, state.w_per_pixel, state.background, state.masks = n_pp, w_pp, background_rgb, masks
+        # the tile renderer was already enqueued by the projection node (right behind the binning, before the host
+        # learned the pair count): this node only ties the image to uv and to the gradient carrier
+        image, state.image = state.image, None
         ctx.state = state
         return image
 
@@ -316,6 +391,7 @@ def rasterize(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_m
         raise TypeError("the fused rasterizer is fp32; use rasterize_unfused for float64 inputs")
     state = _ViewState(profile)
     state.grad_out = grad_out
+    state.background = background_rgb.contiguous()
     cfg = (int(camera.height), int(camera.width), float(near_thresh), float(far_thresh),
            float(cull_mask_padding), float(mh_dist))
     uv, carrier = _ProjectGaussians.apply(
@@ -324,7 +400,7 @@ def rasterize(gaussians, camera_T_world, camera, near_thresh, far_thresh, cull_m
         None if gaussians.sh is None else gaussians.sh.contiguous(),
         camera_T_world.contiguous(), camera.K.contiguous(), state, cfg)
     state.uv_ref = weakref.ref(uv)
-    image = _CompositeTiles.apply(uv, carrier, background_rgb.contiguous(), state)
+    image = _CompositeTiles.apply(uv, carrier, state.background, state)
     culling_mask = state.visible == 0
     if return_state:
         return image, culling_mask, uv, state

@@ -219,10 +219,15 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
 
 /* emits the (tile, depth) keys and original-gaussian ids of all P pairs, the compact list of
  * visible gaussian ids vis_idx int32 [M] and the compacted uv [M,2] the reference returns */
-/* keys are (tile << depth_bits) | depth_key; depth_bits in 1..32 is the number of significant key bits */
+/* keys are (tile << depth_bits) | depth_key; depth_bits in 1..32 is the number of significant key bits.
+ * capacity: 0 when keys / ids hold exactly P entries (the host has read P = scan[N-1] & 0xffffffff); otherwise the
+ * number of entries of SPECULATIVELY sized buffers (the host has not synchronised yet): pairs beyond the capacity
+ * are dropped (the caller finds P > capacity when it does read P, and redoes the binning), positions [P, capacity)
+ * are filled with the all-ones key, which sorts behind every real pair; gsr_sort_*, gsr_tile_ranges and
+ * gsr_gather_records* are then called with `capacity` in place of P and ignore the padding. */
 int gsr_emit_pairs(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
                    const uint64_t* scan, int n_tiles_x, int n_tiles_y, float mh_dist, int depth_bits,
-                   uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, void* stream);
+                   uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, int64_t capacity, void* stream);
 
 size_t gsr_sort_pairs_temp_bytes(int P);
 int gsr_sort_pairs(int P, int n_tiles, int depth_bits, const uint64_t* keys_in, const uint32_t* ids_in,
@@ -247,7 +252,7 @@ int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, 
 int gsr_packed_id_bits(int N, int n_tiles, int depth_bits);
 int gsr_emit_keys(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
                   const uint64_t* scan, int n_tiles_x, int n_tiles_y, float mh_dist, int depth_bits, int id_bits,
-                  uint64_t* keys, int32_t* vis_idx, float* uv_compact, void* stream);
+                  uint64_t* keys, int32_t* vis_idx, float* uv_compact, int64_t capacity, void* stream);
 size_t gsr_sort_keys_temp_bytes(int P);
 int gsr_sort_keys(int P, int n_tiles, int depth_bits, int id_bits, const uint64_t* keys_in, uint64_t* keys_out,
                   void* temp, size_t temp_bytes, void* stream);

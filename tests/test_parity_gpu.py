@@ -410,6 +410,37 @@ def test_contribution_masks_do_not_change_the_gradients():
         assert rel(with_masks[k], without[k]) < 2e-5, (k, rel(with_masks[k], without[k]))  # fp32 atomics noise
 
 
+def test_speculative_pair_buffers_eager_overflow_and_fit_agree():
+    """rasterize() sizes the pair buffers from recent views and reads the real counts only after binning and the
+    tile renderer are enqueued.  Three ways through it must give the same bits: the first view of a kind (eager
+    read), a view whose pair count overflows the guess (both stages run again) and a view that fits (padding keys
+    behind the real pairs)."""
+    from gaussian_splatting_b200 import rasterize as R
+
+    sc = scenes.np_scene(80_000, "720p", sh_degree=1, seed=6, view=2, n_views=3)
+    G = synth.make_upstream_grad("720p").numpy()
+    key = (dev().index if dev().index is not None else torch.cuda.current_device(), 80_000, sc["H"], sc["W"])
+    R._PAIR_HISTORY.pop(key, None)
+    eager = run_b200(sc, G=G)
+    assert len(R._PAIR_HISTORY[key]) == 1
+    P = R._PAIR_HISTORY[key][0]
+    assert P > 200_000
+    R._PAIR_HISTORY[key] = [1000]          # a guess far too small: capacity 66 Ki pairs < P
+    overflow = run_b200(sc, G=G)
+    assert R._PAIR_HISTORY[key][-1] == P
+    R._PAIR_HISTORY[key] = [P]             # capacity = 1.04 P + 64 Ki: fits, with padding behind the real pairs
+    fit = run_b200(sc, G=G)
+    R._PAIR_HISTORY[key] = [2 * P]         # lots of padding
+    loose = run_b200(sc, G=G)
+    for other, name in ((overflow, "overflow"), (fit, "fit"), (loose, "loose")):
+        assert_bits_equal(other["image"], eager["image"], f"image ({name})")
+        assert_bits_equal(other["uv"], eager["uv"], f"uv ({name})")
+        assert_bits_equal(other["culling_mask"], eager["culling_mask"], f"mask ({name})")
+        for k in ("g_xyz", "g_rgb", "g_opacity", "g_scale", "g_quaternion", "g_sh"):
+            assert rel(other[k], eager[k]) < 2e-5, (name, k, rel(other[k], eager[k]))
+    R._PAIR_HISTORY.pop(key, None)
+
+
 def test_native_camera_centre_reproduces_torch_inverse():
     """gsr_camera_centre (one kernel) against torch.inverse (the reference's op, splat_py/rasterize.py:91-93) and
     torch.linalg.inv_ex, bit for bit: the bench's pose ring, identity, random rigid poses, general matrices."""

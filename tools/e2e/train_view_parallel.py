@@ -45,6 +45,10 @@ def main():
     ap.add_argument("--max-gaussians", type=int, default=4250000)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--test-eval-interval", type=int, default=500)
+    ap.add_argument("--optimizer", choices=["flat", "sharded"], default="flat",
+                    help="flat: one NCCL all-reduce(avg) of the flat gradient bucket + gsr_adam_step on the replicated "
+                         "flat buffer; sharded: ONE kernel per rank doing reduce-scatter + Adam + all-gather over NVLink "
+                         "peer memory (gsr_adam_step_sharded), Adam state sharded over the ranks (needs >= 2 ranks)")
     a = ap.parse_args()
 
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -95,9 +99,50 @@ def main():
     n0 = g.xyz.shape[0]
     for name in ("xyz", "quaternion", "scale", "opacity", "rgb"):
         getattr(g, name).requires_grad_(True)
-    opt = FlatAdam.for_gaussians(g, base_lr=config.base_lr, multipliers=mult)
+    sharded = a.optimizer == "sharded"
+    grads_sym = None
+    if sharded:
+        assert world > 1, "--optimizer sharded needs torchrun with at least 2 ranks"
+        import types
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from gaussian_splatting_b200.flat_adam import ShardedFlatAdam, flatten_gaussians, section_ends
+
+        def alloc_sym(n):
+            return symm_mem.empty(int(n), dtype=torch.float32, device=dev)
+
+        params_sym = alloc_sym(section_ends(n0, 0)[-1])
+        flat, ends, names = flatten_gaussians(g, flat=params_sym)
+        grads_sym = alloc_sym(flat.numel())
+        grads_sym.zero_()
+        opt = ShardedFlatAdam(params_sym, grads_sym, ends, [config.base_lr * mult[f] for f in names])
+    else:
+        opt = FlatAdam.for_gaussians(g, base_lr=config.base_lr, multipliers=mult)
     stats = DensificationStats(n0, dev)
-    adc = AdaptiveDensityControl(g, opt, stats, config)
+    adc = AdaptiveDensityControl(g, opt, stats, config, alloc_flat=alloc_sym if sharded else None)
+
+    def relayout(fn):
+        """Run a step that may re-lay-out the parameter buffer (densification, opacity reset, a new SH band).  With
+        the sharded optimizer the Adam state is first gathered to full size, the step runs on a full-state stand-in
+        of the optimizer, and the state is sharded again — over new symmetric buffers if the layout changed."""
+        nonlocal opt, grads_sym
+        if not sharded:
+            return fn()
+        m_full, v_full = opt.full_state()
+        shim = types.SimpleNamespace(p=opt.p, m=m_full, v=v_full, ends=list(opt.ends), lrs=list(opt.lrs))
+        adc.optimizer = shim
+        out = fn()
+        if shim.p is not opt.p:
+            grads_sym = alloc_sym(shim.p.numel())
+            grads_sym.zero_()
+            t = opt.t
+            opt = ShardedFlatAdam(shim.p, grads_sym, shim.ends, shim.lrs)
+            opt.load_full_state(shim.m, shim.v, t)
+        else:
+            opt.load_full_state(shim.m, shim.v, opt.t)
+        adc.optimizer = opt
+        return out
     ssim = StructuralSimilarityIndexMeasure(data_range=1.0).to(dev)
 
     # trainer.py:32-43: every `test_split_ratio`-th image is a test image, uniform sampling over the rest
@@ -124,7 +169,8 @@ def main():
 
     fields = ("xyz", "quaternion", "scale", "opacity", "rgb", "sh")
     curve, adc_log = [], []
-    t_stage = dict(render=0.0, reduce=0.0, adam=0.0, adc=0.0)
+    phase_ms = dict(rasterize_fwd=[], loss_and_backward=[], stats_reduce_adam=[])  # CUDA events, every 50th step
+    t_adc = 0.0
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -143,28 +189,48 @@ def main():
         background = torch.zeros(3, device=dev)
         if config.use_background and i < config.use_background_end:
             background = torch.ones(3, device=dev) * float(i % 255) / 255.0
+        timed = (i % 50 == 25)
+        if timed:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         image, mask, uv, state = rasterize(g, im.camera_T_world, cams[im.camera_id], config.near_thresh,
                                            config.far_thresh, config.cull_mask_padding, config.mh_dist,
-                                           config.use_sh_precompute, background, return_state=True)
+                                           config.use_sh_precompute, background, return_state=True,
+                                           grad_out=grads_sym)
         uv.retain_grad()
+        if timed:
+            ev[1].record()
         l1 = torch.nn.functional.l1_loss(image, im.image)
         ssim_loss = 1.0 - ssim(image.unsqueeze(0).permute(0, 3, 1, 2), im.image.unsqueeze(0).permute(0, 3, 1, 2))
         loss = (1.0 - config.ssim_frac) * l1 + config.ssim_frac * ssim_loss
         loss.backward()
+        if timed:
+            ev[2].record()
         # per-view statistics BEFORE the collective: they are this rank's own view (trainer.py:376-385); the xyz
         # gradient they use is this view's, so they are taken from the still un-averaged buffer
         stats.accumulate(state, uv, g.xyz, cams[im.camera_id].K)
-        bucket = GradientBucket.adopt(state.grad_flat, g)
-        bucket.all_reduce(average=True)
-        opt.step(bucket)
+        if sharded:
+            opt.step()  # barrier, reduce-scatter + Adam + all-gather in one kernel over peer memory, barrier
+        else:
+            bucket = GradientBucket.adopt(state.grad_flat, g)
+            bucket.all_reduce(average=True)
+            opt.step(bucket)
+        if timed:
+            ev[3].record()
+            torch.cuda.synchronize()
+            for k, (a0, a1) in zip(phase_ms, ((0, 1), (1, 2), (2, 3))):
+                phase_ms[k].append(ev[a0].elapsed_time(ev[a1]))
         if config.adaptive_control_start < i < config.adaptive_control_end and i % config.adaptive_control_interval == 0:
+            t_a = time.time()
             all_reduce_statistics([stats.uv_grad_accum, stats.xyz_grad_accum, stats.grad_accum_count])
-            info = adc.adaptive_density_control(i)
+            info = relayout(lambda: adc.adaptive_density_control(i))
+            torch.cuda.synchronize()
+            t_adc += time.time() - t_a
             adc_log.append(dict(iter=i, **{k: info.get(k) for k in ("deleted", "cloned", "split", "n_out")}))
         if config.reset_opacity_start < i < config.reset_opacity_end and i % config.reset_opacity_interval == 0:
-            adc.reset_opacity()
+            relayout(adc.reset_opacity)
         if i > 0 and i % config.add_sh_band_interval == 0:
-            adc.add_sh_band(config.base_lr, config.sh_lr_multiplier)
+            relayout(lambda: adc.add_sh_band(config.base_lr, config.sh_lr_multiplier))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -188,8 +254,14 @@ def main():
             "gaussians_start": n0, "gaussians_end": int(g.xyz.shape[0]), "views": n_img,
             "image": [int(images[0].image.shape[1]), int(images[0].image.shape[0])],
             "replicas_consistent": consistent, "adc_passes": len(adc_log), "adc_last": adc_log[-3:],
-            "optimizer": "FlatAdam (gsr_adam_step) after one NCCL all-reduce(avg) of the flat gradient bucket"
-                         if world > 1 else "FlatAdam (gsr_adam_step)",
+            "adc_seconds_total": round(t_adc, 2),
+            "phase_ms_mean_gpu": {k: round(sum(v) / max(len(v), 1), 3) for k, v in phase_ms.items()},
+            "phase_ms_last_quarter": {k: round(sum(v[-len(v) // 4:]) / max(len(v[-len(v) // 4:]), 1), 3)
+                                      for k, v in phase_ms.items()},
+            "optimizer": ("ShardedFlatAdam: gsr_adam_step_sharded (reduce-scatter + Adam + all-gather over NVLink peer "
+                          "memory in one kernel, Adam state sharded)") if sharded else
+                         ("FlatAdam (gsr_adam_step) after one NCCL all-reduce(avg) of the flat gradient bucket"
+                          if world > 1 else "FlatAdam (gsr_adam_step)"),
             "device": torch.cuda.get_device_name(local),
         }
         real_stdout.write("E2E " + json.dumps(line) + "\n")
