@@ -312,19 +312,26 @@ def run_b200(args, rank, world, local):
         alg_bytes = 76.0 * P_used + 20.0 * H * W
         dur_ms = stages.get("render_bwd", float("nan"))
         achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tf = ROOT / "profiles" / "ncu_traffic_latest.json"
         if tf.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-            traffic = json.loads(tf.read_text()).get("k_render_bwd", {}).get("dram_bytes_per_launch")
+            rec = json.loads(tf.read_text()).get("k_render_bwd", {})
+            traffic, traffic_src = rec.get("dram_bytes_per_launch"), rec.get("source")
         # the per-gaussian kernels ARE HBM-bound; report them next to the (issue-bound) dominant kernel
         N_, M_ = st.N, st.M
         other = []
+        # bytes the kernels actually have to move (their own byte model, larger than SURVEY.md 8(d)'s 236 N + 44 M,
+        # which counts neither the 48-byte record + key + flag + scan a kernel writes per gaussian nor the
+        # backward's re-read of the geometry parameters): fwd 236 N read + 61 M + 13 N written; bwd 57 N + 36 M read +
+        # 236 N written
         for kname, stage, nbytes in (("k_preprocess_fwd", "preprocess_fwd", 236.0 * N_ + 61.0 * M_ + 13.0 * N_),
                                      ("k_preprocess_bwd", "preprocess_bwd", (56.0 + 1.0) * N_ + 36.0 * M_ + 236.0 * N_)):
             if stage in stages:
                 ach = nbytes / (stages[stage] * 1e-3) / 1e9
                 other.append(dict(kernel=kname, bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
                                   algorithmic_bytes=nbytes, duration_ms=stages[stage],
+                                  byte_model="kernel's own (see bench.py); SURVEY.md 8(d) counts 236 N + 44 M (fwd), "
+                                             "36 M + 472 N (bwd)",
                                   note="stage time includes the kernel's cub scan / output allocation"))
         # instruction-issue roofline of the same kernel: warp instructions per launch from the committed ncu
         # capture / live duration, against 148 SMs x 4 schedulers x max SM clock
@@ -340,9 +347,10 @@ def run_b200(args, rank, world, local):
                         frac=achieved / peak, traffic=traffic,
                         peak_source="MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                         algorithmic_bytes=alg_bytes, duration_ms=dur_ms,
-                        note="76 B per (gaussian,tile) pair the kernel has to visit + 20 B per pixel; the kernel is "
-                             "instruction-issue bound (ncu: issue slots 77% busy, FMA / ALU pipes ~50%, DRAM 5% of peak; "
-                             "profiles/r01_ncu_full_render_kernels_v7.json), so frac is small by construction",
+                        note="76 B per (gaussian,tile) pair the kernel has to visit + 20 B per pixel (SURVEY.md 8(d)); "
+                             "the kernel is instruction-issue bound, not HBM bound (see issue_roofline and the ncu "
+                             "capture named in traffic_source), so frac is small by construction",
+                        traffic_source=traffic_src,
                         issue_roofline=issue, other_kernels=other)
 
     cpu = None
