@@ -47,7 +47,7 @@ def main():
             if k in col:
                 entry[k] = f"{r[col[k]]} {units[col[k]]}".strip()
         summary.append(entry)
-        short = name.split("(")[0].split("<")[0]
+        short = name.split("(")[0].split("<")[0].replace("void ", "").strip()  # "void k_render_bwd<1>(...)" -> k_render_bwd
 
         def to_bytes(key):
             return float(r[col[key]].replace(",", "")) * _BYTES.get(units[col[key]], 1.0)

@@ -1,7 +1,8 @@
 """Minimal workload for ncu: a few fwd+bwd steps of the bench configuration (3M gaussians, 1080p, SH 3).
 
-    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \\
-        python tools/profile_step.py --steps 3
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \\
+        --log-file gpurun_out/launches.csv python tools/profile_step.py --steps 3
+    (profiling starts after one warm-up step: the first step also runs the one-time per-device self-checks)
     ncu --set full --clock-control none --import-source on -k regex:k_render_bwd -s 1 -c 1 \\
         -o gpurun_out/prof_render_bwd python tools/profile_step.py --steps 2
 """
@@ -28,7 +29,10 @@ def main():
     cam = synth.make_camera(args.res, device=dev)
     G = synth.make_upstream_grad(args.res, device=dev)
     bg = torch.full((3,), 0.5, device=dev)
-    for i in range(args.steps):
+    for i in range(-1, args.steps):
+        if i == 0:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()  # honoured by `ncu --profile-from-start off`; a no-op otherwise
         T = synth.make_pose(i % 8, 8, device=dev)
         for p in (g.xyz, g.rgb, g.opacity, g.scale, g.quaternion, g.sh):
             p.grad = None
@@ -37,6 +41,7 @@ def main():
         image.backward(G)
         torch.cuda.nvtx.range_pop()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     print("done", float(image.mean()))
 
 
