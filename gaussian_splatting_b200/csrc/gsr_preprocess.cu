@@ -264,8 +264,11 @@ __global__ void __launch_bounds__(PRE_THREADS, 7)
 
 // Fused VJP.  g_rgb/g_opa/g_uv/g_conic are the per-Gaussian sums produced by the render backward
 // (indexed by original gaussian).  Order of the chain: SURVEY.md Appendix A "Per-Gaussian backward".
+#ifndef GSR_PRE_BWD_MINB
+#define GSR_PRE_BWD_MINB 6
+#endif
 template <int N_SH, bool HAS_SH>
-__global__ void __launch_bounds__(PRE_THREADS, 6)
+__global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_BWD_MINB)
     k_preprocess_bwd(int N, const float* __restrict__ xyz, const float* __restrict__ quat,
                      const float* __restrict__ scale, const float* __restrict__ opa_logit,
                      const float* __restrict__ Tdev, const float* __restrict__ Kdev,

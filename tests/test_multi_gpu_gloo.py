@@ -115,3 +115,57 @@ def test_gradient_bucket_all_reduce_two_ranks():
         assert p.exitcode == 0
     assert err_attach < 1e-5 and err_adopt < 1e-5 and err_copy < 1e-5
     assert stat == 3.0  # 1 + 2
+
+
+def _adc_worker(rank, world, port, out):
+    """Densification with several ranks: per-view statistics differ per rank, are summed right before a pass
+    (all_reduce_statistics), and every rank must then take IDENTICAL decisions (same plan, same random split samples)
+    — that is what keeps the replicas of tools/e2e/train_view_parallel.py bit-identical."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gaussian_splatting_b200.densify import DensificationStats, DensifyConfig, plan_adaptive_density_control
+        from gaussian_splatting_b200.structs import Gaussians
+        from gaussian_splatting_b200.view_parallel import all_reduce_statistics
+
+        n = 3000
+        g0 = torch.Generator().manual_seed(0)                      # replicated parameters
+        P = dict(xyz=torch.randn(n, 3, generator=g0), quaternion=torch.randn(n, 4, generator=g0),
+                 scale=torch.randn(n, 3, generator=g0) * 1.2 - 4.0, opacity=torch.randn(n, 1, generator=g0) * 2.0 - 1.0,
+                 rgb=torch.randn(n, 3, generator=g0), sh=torch.randn(n, 3, 3, generator=g0) * 0.1)
+        g = Gaussians(P["xyz"], P["rgb"], P["opacity"], P["scale"], P["quaternion"], P["sh"])
+        gr = torch.Generator().manual_seed(100 + rank)             # this rank's own views
+        stats = DensificationStats.__new__(DensificationStats)
+        stats.grad_accum_count = torch.randint(0, 3, (n,), generator=gr, dtype=torch.int32)
+        stats.uv_grad_accum = torch.rand(n, 2, generator=gr) * 1e-3 * (stats.grad_accum_count > 0).unsqueeze(1)
+        stats.xyz_grad_accum = torch.rand(n, 3, generator=gr) * 1e-3
+        local_count = stats.grad_accum_count.clone()
+        all_reduce_statistics([stats.uv_grad_accum, stats.xyz_grad_accum, stats.grad_accum_count])
+        torch.manual_seed(7)                                       # same random streams on every rank
+        plan = plan_adaptive_density_control(g, stats, DensifyConfig(), 1200)
+        sig = torch.cat([plan.src.double(), plan.clone_row.double(), plan.split_row.double(),
+                         plan.xyz_add.reshape(-1).double(), plan.xyz_sub.reshape(-1).double()])
+        lo, hi = sig.clone(), sig.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        total = local_count.clone()
+        dist.all_reduce(total)
+        if rank == 0:
+            out.put((bool(torch.equal(lo, hi)), bool(torch.equal(total, stats.grad_accum_count)), plan.info))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_densification_plan_is_identical_on_every_rank():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, _free_port()
+    procs = [ctx.Process(target=_adc_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    same_plan, counts_summed, info = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same_plan and counts_summed
+    assert info["deleted"] > 0 and info["cloned"] > 0 and info["split"] > 0, info
