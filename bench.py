@@ -42,8 +42,8 @@ N_GAUSS = 3_000_000
 RES = "1080p"
 SH_DEGREE = 3
 N_POSES = 8
-MY_KERNELS = ["k_camera_centre", "k_preprocess_fwd", "k_emit_pairs_fused", "k_tile_ranges", "k_gather_records_keys",
-              "k_render_fwd", "k_render_bwd", "k_preprocess_bwd"]
+MY_KERNELS = ["k_camera_centre", "k_preprocess_fwd", "k_emit_pairs_fused", "k_tile_ranges", "k_render_fwd",
+              "k_render_bwd", "k_preprocess_bwd"]  # + k_gather_records_keys with GSR_RECORD_STREAM=1
 
 
 def log(msg):
@@ -380,7 +380,8 @@ def run_b200(args, rank, world, local):
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
         "per_rank": {"ms_per_step": per_rank_res, "e2e_ms_per_step": per_rank_e2e, "sm_mhz": per_rank_clocks,
                      "note": "value / e2e use the MAX over ranks; ranks differ by their GPU's clocks under load"},
-        "gpu_launches": len(MY_KERNELS) * args.steps, "kernels": MY_KERNELS,
+        "gpu_launches": (len(MY_KERNELS) + (1 if os.environ.get("GSR_RECORD_STREAM", "0") == "1" else 0)) * args.steps,
+        "kernels": MY_KERNELS,
         "roofline": roofline, "cpu_baseline": cpu, "impl": "b200",
     }
     emit(line)

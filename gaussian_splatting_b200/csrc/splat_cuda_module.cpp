@@ -473,9 +473,12 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
 // speculative = true: M and P are CAPACITIES (the host has not read the real counts yet): buffers are sized by
 // them, the pair buffer is padded behind the real pairs (gsr_emit_*'s `capacity`), and every tensor is returned at
 // full capacity — the caller narrows them once it knows M and P, and redoes the call if P exceeded the capacity.
-std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_bin(
+// no_stream = true: the tile kernels will fetch records through the sorted pair list themselves
+// (gsr_render_*_gather): no record stream is produced; returns the sorted keys (and id_bits) instead.
+// returns (ids_sorted, ranges, stream_rec, vis_idx, uv, keys_sorted, id_bits)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, int64_t> fused_bin(
     torch::Tensor records, torch::Tensor zkey, torch::Tensor visible, torch::Tensor scan, int64_t M, int64_t P,
-    int64_t H, int64_t W, double mh_dist, int64_t depth_bits, bool speculative) {
+    int64_t H, int64_t W, double mh_dist, int64_t depth_bits, bool speculative, bool no_stream) {
     const int N = records.size(0);
     const int ntx = (W + 15) / 16, nty = (H + 15) / 16, n_tiles = ntx * nty;
     c10::cuda::CUDAGuard guard(records.device());
@@ -483,11 +486,13 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
     auto i32 = opt.dtype(torch::kInt32);
     const int64_t Pa = std::max<int64_t>(P, 1);
     torch::Tensor keys = torch::empty({2 * Pa}, opt.dtype(torch::kInt64));
-    torch::Tensor ids_sorted = torch::empty({Pa}, i32);
+    const int id_bits_probe = gsr_packed_id_bits(N, n_tiles, (int)depth_bits);
+    // with the id in the key and no stream, nobody needs the separate id array
+    torch::Tensor ids_sorted = torch::empty({(no_stream && id_bits_probe > 0) ? 0 : Pa}, i32);
     torch::Tensor vis_idx = torch::empty({M}, i32);
     torch::Tensor uv = torch::empty({M, 2}, opt);
     torch::Tensor ranges = torch::empty({n_tiles + 1}, i32);
-    torch::Tensor stream_rec = torch::empty({Pa, GSR_REC_FLOATS}, opt);
+    torch::Tensor stream_rec = torch::empty({no_stream ? 0 : Pa, GSR_REC_FLOATS}, opt);
     uint64_t* keys_a = (uint64_t*)keys.data_ptr<int64_t>();
     uint64_t* keys_b = keys_a + Pa;
     const int id_bits = gsr_packed_id_bits(N, n_tiles, (int)depth_bits);
@@ -505,9 +510,10 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
         check_rc(gsr_tile_ranges((int)P, n_tiles, (int)depth_bits + id_bits, keys_b, ranges.data_ptr<int>(),
                                  cur_stream()),
                  "gsr_tile_ranges");
-        check_rc(gsr_gather_records_keys((int)P, id_bits, keys_b, F32PTR(records), F32PTR(stream_rec),
-                                         ids_sorted.data_ptr<int>(), nullptr, cur_stream()),
-                 "gsr_gather_records_keys");
+        if (!no_stream)
+            check_rc(gsr_gather_records_keys((int)P, id_bits, keys_b, F32PTR(records), F32PTR(stream_rec),
+                                             ids_sorted.data_ptr<int>(), nullptr, cur_stream()),
+                     "gsr_gather_records_keys");
     } else {
         torch::Tensor ids = torch::empty({Pa}, i32);
         check_rc(gsr_emit_pairs(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(),
@@ -522,17 +528,23 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
                  "gsr_sort_pairs");
         check_rc(gsr_tile_ranges((int)P, n_tiles, (int)depth_bits, keys_b, ranges.data_ptr<int>(), cur_stream()),
                  "gsr_tile_ranges");
-        check_rc(gsr_gather_records((int)P, (const uint32_t*)ids_sorted.data_ptr<int>(), F32PTR(records),
-                                    F32PTR(stream_rec), nullptr, nullptr, cur_stream()),
-                 "gsr_gather_records");
+        if (!no_stream)
+            check_rc(gsr_gather_records((int)P, (const uint32_t*)ids_sorted.data_ptr<int>(), F32PTR(records),
+                                        F32PTR(stream_rec), nullptr, nullptr, cur_stream()),
+                     "gsr_gather_records");
     }
-    return std::make_tuple(ids_sorted.narrow(0, 0, P), ranges, stream_rec, vis_idx, uv);
+    torch::Tensor keys_sorted = (no_stream && id_bits > 0) ? keys.narrow(0, Pa, Pa) : torch::empty({0}, opt.dtype(torch::kInt64));
+    return std::make_tuple(ids_sorted.numel() > 0 ? ids_sorted.narrow(0, 0, P) : ids_sorted, ranges, stream_rec, vis_idx,
+                           uv, keys_sorted, (int64_t)id_bits);
 }
 
 // image [H,W,3], n [H,W] i32, wlast [H,W], contribution masks (i32 words; empty when record_masks is false)
+// records: the record stream [P,12] — or, when keys_sorted / ids_sorted name the sorted pair list (gather mode), the
+// per-gaussian record array [N,12]
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_render_forward(
     torch::Tensor stream_rec, torch::Tensor ranges, torch::Tensor background, int64_t H, int64_t W, int64_t P,
-    bool record_masks) {
+    bool record_masks, c10::optional<torch::Tensor> keys_sorted, c10::optional<torch::Tensor> ids_sorted,
+    int64_t id_bits, bool gather) {
     CHECK_VALID_INPUT(background); CHECK_FLOAT_TENSOR(background);
     TORCH_CHECK(background.numel() == 3, "Background RGB must have 3 elements");
     c10::cuda::CUDAGuard guard(stream_rec.device());
@@ -543,10 +555,21 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_ren
     torch::Tensor masks = record_masks
                               ? torch::zeros({(int64_t)gsr_contribution_mask_words(P, (int)H, (int)W)}, opt.dtype(torch::kInt32))
                               : torch::empty({0}, opt.dtype(torch::kInt32));
-    check_rc(gsr_render_forward(F32PTR(stream_rec), ranges.data_ptr<int>(), F32PTR(background), (int)H, (int)W,
-                                n.data_ptr<int>(), F32PTR(w), F32PTR(image),
-                                record_masks ? (uint32_t*)masks.data_ptr<int>() : nullptr, cur_stream()),
-             "gsr_render_forward");
+    uint32_t* mptr = record_masks ? (uint32_t*)masks.data_ptr<int>() : nullptr;
+    if (gather) {
+        const bool by_key = keys_sorted.has_value() && keys_sorted->numel() > 0;
+        TORCH_CHECK(by_key || (ids_sorted.has_value() && ids_sorted->numel() > 0) || P == 0, "gather mode needs the sorted pair list");
+        check_rc(gsr_render_forward_gather(F32PTR(stream_rec),
+                                           by_key ? (const uint64_t*)keys_sorted->data_ptr<int64_t>() : nullptr, (int)id_bits,
+                                           (!by_key && ids_sorted.has_value() && ids_sorted->numel() > 0) ? ids_sorted->data_ptr<int>() : nullptr,
+                                           ranges.data_ptr<int>(), F32PTR(background), (int)H, (int)W, n.data_ptr<int>(),
+                                           F32PTR(w), F32PTR(image), mptr, cur_stream()),
+                 "gsr_render_forward_gather");
+    } else {
+        check_rc(gsr_render_forward(F32PTR(stream_rec), ranges.data_ptr<int>(), F32PTR(background), (int)H, (int)W,
+                                    n.data_ptr<int>(), F32PTR(w), F32PTR(image), mptr, cur_stream()),
+                 "gsr_render_forward");
+    }
     return std::make_tuple(image, n, w, masks);
 }
 
@@ -554,7 +577,8 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_ren
 // gaussian; zero-filled, then accumulated into by the render backward
 torch::Tensor fused_render_backward(torch::Tensor grad_image, int64_t N, torch::Tensor stream_rec,
                                     torch::Tensor ids_sorted, torch::Tensor ranges, torch::Tensor background,
-                                    torch::Tensor n, torch::Tensor w, torch::Tensor masks) {
+                                    torch::Tensor n, torch::Tensor w, torch::Tensor masks,
+                                    c10::optional<torch::Tensor> keys_sorted, int64_t id_bits, bool gather) {
     CHECK_VALID_INPUT(grad_image); CHECK_FLOAT_TENSOR(grad_image);
     const int H = n.size(0), W = n.size(1);
     TORCH_CHECK(grad_image.dim() == 3 && grad_image.size(0) == H && grad_image.size(1) == W &&
@@ -566,11 +590,21 @@ torch::Tensor fused_render_backward(torch::Tensor grad_image, int64_t N, torch::
     float* g_opa = g_rgb + (size_t)N * 3;
     float* g_uv = g_opa + (size_t)N;
     float* g_conic = g_uv + (size_t)N * 2;
-    check_rc(gsr_render_backward(F32PTR(stream_rec), ids_sorted.data_ptr<int>(), ranges.data_ptr<int>(),
-                                 F32PTR(background), H, W, n.data_ptr<int>(), F32PTR(w), F32PTR(grad_image),
-                                 g_rgb, g_opa, g_uv, g_conic,
-                                 masks.numel() > 0 ? (const uint32_t*)masks.data_ptr<int>() : nullptr, cur_stream()),
-             "gsr_render_backward");
+    const uint32_t* mptr = masks.numel() > 0 ? (const uint32_t*)masks.data_ptr<int>() : nullptr;
+    if (gather) {
+        const bool by_key = keys_sorted.has_value() && keys_sorted->numel() > 0;
+        check_rc(gsr_render_backward_gather(F32PTR(stream_rec),
+                                            by_key ? (const uint64_t*)keys_sorted->data_ptr<int64_t>() : nullptr, (int)id_bits,
+                                            (!by_key && ids_sorted.numel() > 0) ? ids_sorted.data_ptr<int>() : nullptr,
+                                            ranges.data_ptr<int>(), F32PTR(background), H, W, n.data_ptr<int>(), F32PTR(w),
+                                            F32PTR(grad_image), g_rgb, g_opa, g_uv, g_conic, mptr, cur_stream()),
+                 "gsr_render_backward_gather");
+    } else {
+        check_rc(gsr_render_backward(F32PTR(stream_rec), ids_sorted.data_ptr<int>(), ranges.data_ptr<int>(),
+                                     F32PTR(background), H, W, n.data_ptr<int>(), F32PTR(w), F32PTR(grad_image),
+                                     g_rgb, g_opa, g_uv, g_conic, mptr, cur_stream()),
+                 "gsr_render_backward");
+    }
     return slab;
 }
 

@@ -51,6 +51,10 @@ IN_KERNEL_TRANSFORM = os.environ.get("GSR_TORCH_TRANSFORM", "0") != "1"
 # the forward records which (8x4 pixel block, splat) pairs contributed; the backward then visits exactly those
 # (GSR_NO_MASKS=1: the backward redoes the forward's conservative footprint test instead)
 USE_CONTRIBUTION_MASKS = os.environ.get("GSR_NO_MASKS", "0") != "1"
+# the tile kernels fetch their records through the sorted pair list themselves (cp.async gather); with
+# GSR_RECORD_STREAM=1 a separate kernel first writes the depth-sorted, tile-contiguous record stream they then read
+# with bulk copies (the round-1 arrangement)
+USE_RECORD_GATHER = os.environ.get("GSR_RECORD_STREAM", "0") != "1"
 IN_KERNEL_TRANSFORM_MIN_N = 16384
 CUBLAS_BATCH_CHUNK = 65535   # gridDim limit cuBLAS batches against
 SMALL_BATCH = 1024           # chunks below ~300 use another kernel (measured: 100 differs, 300 matches)
@@ -202,8 +206,19 @@ def _depth_key_params(near, far):
 class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
-    __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "ids_sorted", "ranges", "stream_rec",
+    __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "_ids_sorted", "ranges", "stream_rec", "gather",
+                 "records", "keys_sorted", "id_bits",
                  "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "vis_idx32", "scan", "masks", "uv_ref", "uv_grad_emitted", "image", "speculation_overflowed")
+
+    @property
+    def ids_sorted(self):
+        """int32 [P]: gaussian id of every sorted (gaussian, tile) pair (the reference's
+        `sorted_gaussian_idx_by_splat_idx`).  When the id rides in the sort key and the tile kernels gather through
+        the keys, nobody writes this array: it is extracted on demand."""
+        if self._ids_sorted is not None and self._ids_sorted.numel() == 0 and self.P > 0 and self.keys_sorted is not None:
+            mask = (1 << self.id_bits) - 1
+            self._ids_sorted = (self.keys_sorted[:self.P] & mask).to(torch.int32)
+        return self._ids_sorted
 
     def __init__(self, profile=None):
         self.profile = profile  # optional list: (stage name, start event, end event) per native call
@@ -278,11 +293,14 @@ class _ProjectGaussians(torch.autograd.Function):
                                    "the int32 pair index of the native path (P must be < 2^31)")
             return M_, P_
 
+        gather = USE_RECORD_GATHER
+
         def bin_and_render(M_, P_, speculative):
             with _stage(state, "bin_sort_gather"):
-                binned = ext.fused_bin(records, zkey, visible, scan, M_, P_, H, W, mh, depth_bits, speculative)
+                binned = ext.fused_bin(records, zkey, visible, scan, M_, P_, H, W, mh, depth_bits, speculative, gather)
             with _stage(state, "render_fwd"):
-                rendered = ext.fused_render_forward(binned[2], binned[1], background, H, W, P_, record_masks)
+                rendered = ext.fused_render_forward(records if gather else binned[2], binned[1], background, H, W, P_,
+                                                    record_masks, binned[5], binned[0], binned[6], gather)
             return binned, rendered
 
         # The host needs M and P (the shape of the returned uv; the size of the pair buffers).  Reading them right
@@ -310,15 +328,17 @@ class _ProjectGaussians(torch.autograd.Function):
                 binned, rendered = bin_and_render(M, P, False)
                 state.speculation_overflowed = True
             else:
-                ids_c, ranges_c, stream_c, vis_c, uv_c = binned
-                binned = (ids_c.narrow(0, 0, P), ranges_c, stream_c, vis_c.narrow(0, 0, M), uv_c.narrow(0, 0, M))
+                ids_c, ranges_c, stream_c, vis_c, uv_c, keys_c, idb = binned
+                binned = (ids_c.narrow(0, 0, P) if ids_c.numel() else ids_c, ranges_c, stream_c, vis_c.narrow(0, 0, M),
+                          uv_c.narrow(0, 0, M), keys_c, idb)
         _note_pairs(key, P)
-        ids_sorted, ranges, stream_rec, vis_idx, uv = binned
+        ids_sorted, ranges, stream_rec, vis_idx, uv, keys_sorted, id_bits = binned
+        state.gather, state.records, state.keys_sorted, state.id_bits = gather, records, keys_sorted, int(id_bits)
         state.image, state.n_per_pixel, state.w_per_pixel, state.masks = rendered
         state.N, state.M, state.P, state.H, state.W = xyz.shape[0], M, P, H, W
         state.visible = visible
         state.vis_idx = state.vis_idx32 = vis_idx                # int32 [M]: visible gaussians, ascending
-        state.ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec
+        state._ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec
         state.scan = scan
         carrier = torch.empty(9 * xyz.shape[0], dtype=xyz.dtype, device=xyz.device)
         ctx.state = state
@@ -366,8 +386,10 @@ class _CompositeTiles(torch.autograd.Function):
     def backward(ctx, grad_image):
         st = ctx.state
         with _stage(st, "render_bwd"):
-            slab = native().fused_render_backward(grad_image.contiguous(), st.N, st.stream_rec, st.ids_sorted,
-                                                  st.ranges, st.background, st.n_per_pixel, st.w_per_pixel, st.masks)
+            slab = native().fused_render_backward(grad_image.contiguous(), st.N,
+                                                  st.records if st.gather else st.stream_rec, st._ids_sorted,
+                                                  st.ranges, st.background, st.n_per_pixel, st.w_per_pixel, st.masks,
+                                                  st.keys_sorted, st.id_bits, st.gather)
         # The render pass's gradient on the compact uv is a gather of the slab's uv section (28 us at 3M).  It
         # reaches the per-gaussian backward through the slab anyway, so it is only materialised when it can be
         # OBSERVED: the caller retained uv's gradient (the reference trainer does, splat_py/trainer.py:360) or

@@ -154,6 +154,22 @@ int gsr_render_backward(const float* records, const int32_t* sorted_gaussian_idx
                         const float* grad_image, float* grad_rgb, float* grad_opacity,
                         float* grad_uv, float* grad_conic, const uint32_t* contribution_masks, void* stream);
 
+/* The same two kernels WITHOUT a record stream: the tile kernels fetch each batch's records themselves from the
+ * per-gaussian record array gaussian_records [N,12] (gsr_preprocess_forward's output), through the sorted pair list
+ * — keys_sorted (gaussian id in the low id_bits of every key, gsr_sort_keys' output) or ids_sorted (gsr_sort_pairs'
+ * id output); exactly one of the two is non-NULL.  3 x 16-byte cp.async per record, issued by the warp that recycles
+ * a pipeline stage, completion on the stage's mbarrier; gsr_gather_records* and the [P,12] stream are not needed.
+ * Gradient rows are indexed by gaussian id. */
+int gsr_render_forward_gather(const float* gaussian_records, const uint64_t* keys_sorted, int id_bits,
+                              const int32_t* ids_sorted, const int32_t* tile_ranges, const float* background_rgb, int H,
+                              int W, int32_t* num_splats_per_pixel, float* final_weight_per_pixel, float* image,
+                              uint32_t* contribution_masks, void* stream);
+int gsr_render_backward_gather(const float* gaussian_records, const uint64_t* keys_sorted, int id_bits,
+                               const int32_t* ids_sorted, const int32_t* tile_ranges, const float* background_rgb, int H,
+                               int W, const int32_t* num_splats_per_pixel, const float* final_weight_per_pixel,
+                               const float* grad_image, float* grad_rgb, float* grad_opacity, float* grad_uv,
+                               float* grad_conic, const uint32_t* contribution_masks, void* stream);
+
 /* General renderers: any dtype, any n_sh in {1,4,9,16} (per-pixel SH via view_dir_by_pixel
  * [H,W,3]); same semantics as the reference's template instantiations
  * (fp64: no +0.25 dilation, exp(), no 1/255 skip — src/render.cu:117-148). */

@@ -51,8 +51,10 @@ def test_library_is_sm100a_only_and_has_tma():
     elfs = subprocess.run(["cuobjdump", "-lelf", str(so)], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", elfs))
     assert archs == {"100a"}, archs
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3gsr12k_render_fwdILb1EEEvPKfPKiS2_iiPiPfS6_Pj", str(so)],
-                          capture_output=True, text=True).stdout
+    names = subprocess.run(["cuobjdump", "-sass", str(so)], capture_output=True, text=True).stdout
+    fwd = re.findall(r"Function : (\S*k_render_fwdILb1ELb0\S*)", names)  # masks on, record stream by bulk copies
+    assert fwd, "k_render_fwd<true, false> not in the library"
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", fwd[0], str(so)], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass, "render forward kernel should stage records with TMA bulk copies (UBLKCP)"
 
 

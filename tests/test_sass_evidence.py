@@ -39,10 +39,20 @@ def find(counts, fragment):
 def test_tile_kernels_use_packed_fp32_and_tma():
     counts = sass_counts()
     for k in ("k_render_fwd", "k_render_bwd"):
-        c = find(counts, f"gsr{len(k)}{k}ILb1E")  # itanium mangling: N3gsr<len><name>I<template args>E (masks on)
+        c = find(counts, f"gsr{len(k)}{k}ILb1ELb0E")  # N3gsr<len><name>I<template args>E: masks on, record stream
         assert c["FFMA2"] >= 10 and c["FMUL2"] >= 10, (k, dict(c))      # two pixels per lane, packed arithmetic
         assert c["UBLKCP"] >= 1 and c["SYNCS"] >= 1, (k, dict(c))        # record batches arrive by TMA + mbarrier
         assert c["BAR"] <= 4, (k, dict(c))                               # no CTA barrier in the batch loops (setup only)
+
+
+def test_gather_variants_fetch_records_with_cp_async_on_the_stage_barrier():
+    """The default tile kernels take no record stream: the warp that recycles a stage gathers the batch's records
+    with 16-byte cp.async (SASS LDGSTS) and signals the stage's mbarrier (SYNCS / ARRIVES)."""
+    counts = sass_counts()
+    for k in ("k_render_fwd", "k_render_bwd"):
+        c = find(counts, f"gsr{len(k)}{k}ILb1ELb1E")
+        assert c["LDGSTS"] >= 3 and c["SYNCS"] >= 1, (k, dict(c))
+        assert c["FFMA2"] >= 10 and c["BAR"] <= 4, (k, dict(c))
 
 
 def test_per_gaussian_kernels_stage_through_tma():
