@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(BIN_THREADS)
                        const uint32_t* __restrict__ zkey, const uint8_t* __restrict__ visible,
                        const uint64_t* __restrict__ scan, int ntx, int nty, float mh, int depth_bits,
                        int id_bits, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
-                       int32_t* __restrict__ vis_idx, float* __restrict__ uv_compact, int64_t cap) {
+                       int32_t* __restrict__ vis_idx, float* __restrict__ uv_compact, int64_t cap,
+                       const uint64_t* __restrict__ tile_mask, const uint32_t* __restrict__ tile_win) {
     const int i = blockIdx.x * BIN_THREADS + threadIdx.x;
     if (cap > 0) {
         // Speculatively sized buffers (the host has not read P yet): positions [P, cap) get the all-ones key, which
@@ -108,6 +109,33 @@ __global__ void __launch_bounds__(BIN_THREADS)
     uv_compact[rank * 2 + 0] = u;
     uv_compact[rank * 2 + 1] = v;
     if (cnt == 0) return;
+    const uint32_t win = (tile_win != nullptr) ? tile_win[i] : 0xffffffffu;
+    if (win != 0xffffffffu) {
+        // the per-gaussian stage already tested this gaussian's tile window: expand its hit mask (ascending bit =
+        // the enumeration order of walk_tiles: x-major, then y)
+        uint64_t m = tile_mask[i];
+        const int x0 = (int)(win & 0xffu), y0 = (int)((win >> 8) & 0xffu), wy = (int)(win >> 24);
+        const uint64_t z = zkey[i];
+        const int64_t base = (int64_t)(prev & 0xffffffffu);
+        const int64_t lim = cap > 0 ? cap : INT64_MAX;
+        int n = 0;
+        while (m) {
+            const int b = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const int tx = x0 + b / wy, ty = y0 + b % wy;
+            if (base + n < lim) {
+                const uint64_t k = ((uint64_t)(uint32_t)(ty * ntx + tx) << depth_bits) | z;
+                if (id_bits > 0) {
+                    keys[base + n] = (k << id_bits) | (uint32_t)i;
+                } else {
+                    keys[base + n] = k;
+                    ids[base + n] = (uint32_t)i;
+                }
+            }
+            ++n;
+        }
+        return;
+    }
     Obb o;
     const float* r = records + (size_t)i * REC;
     compute_obb(u, v, r[R_A], __fmul_rn(r[R_B2], 0.5f), r[R_C], mh, o);
@@ -290,11 +318,12 @@ int gsr_binning_emit_sort(int N, int P, const float* uvs, const float* xyz_cam, 
 int gsr_emit_pairs(int N, const float* records, const uint32_t* depth_key,
                    const uint8_t* visible, const uint64_t* scan, int ntx, int nty, float mh, int depth_bits,
                    uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, int64_t capacity,
-                   void* stream) {
+                   const uint64_t* tile_mask, const uint32_t* tile_win, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
+    if ((tile_mask == nullptr) != (tile_win == nullptr)) return GSR_ERR_BAD_ARG;
     k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, depth_bits, 0, keys,
-                                     ids, vis_idx, uv_compact, capacity);
+                                     ids, vis_idx, uv_compact, capacity, tile_mask, tile_win);
     return (int)cudaGetLastError();
 }
 
@@ -307,12 +336,14 @@ int gsr_packed_id_bits(int N, int n_tiles, int depth_bits) {
 
 int gsr_emit_keys(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
                   const uint64_t* scan, int ntx, int nty, float mh, int depth_bits, int id_bits, uint64_t* keys,
-                  int32_t* vis_idx, float* uv_compact, int64_t capacity, void* stream) {
+                  int32_t* vis_idx, float* uv_compact, int64_t capacity, const uint64_t* tile_mask,
+                  const uint32_t* tile_win, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
     if (id_bits < 1 || id_bits != gsr_packed_id_bits(N, ntx * nty, depth_bits)) return GSR_ERR_BAD_ARG;
+    if ((tile_mask == nullptr) != (tile_win == nullptr)) return GSR_ERR_BAD_ARG;
     k_emit_pairs_fused<<<BGRID(N)>>>(N, records, depth_key, visible, scan, ntx, nty, mh, depth_bits, id_bits, keys,
-                                     nullptr, vis_idx, uv_compact, capacity);
+                                     nullptr, vis_idx, uv_compact, capacity, tile_mask, tile_win);
     return (int)cudaGetLastError();
 }
 

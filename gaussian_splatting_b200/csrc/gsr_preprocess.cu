@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(PRE_THREADS, 7)
                      const float* __restrict__ camdev, float width, float height, float near_t, float far_t,
                      float pad, float mh, int ntx, int nty, uint32_t depth_base,
                      float* __restrict__ records, uint32_t* __restrict__ zkey,
-                     uint8_t* __restrict__ visible, uint64_t* __restrict__ packed, int use_tma) {
+                     uint8_t* __restrict__ visible, uint64_t* __restrict__ packed, uint64_t* __restrict__ tile_mask,
+                     uint32_t* __restrict__ tile_win, int use_tma) {
     constexpr int NR3 = HAS_SH ? 3 * (N_SH - 1) : 1;
     __shared__ ViewConsts vc;
     __shared__ __align__(128) float s_sh[PRE_THREADS * NR3];       // SH coefficients of the CTA's gaussians
@@ -230,14 +231,29 @@ __global__ void __launch_bounds__(PRE_THREADS, 7)
             compute_obb(u, v, rec[R_A], __fmul_rn(rec[R_B2], 0.5f), rec[R_C], mh, ob);
             int x0, x1, y0, y1, c = 0;
             tile_window(u, v, ob.radius_tiles, ntx, nty, x0, x1, y0, y1);
+            // The tiles hit are remembered as a bit mask over the window (bit = (tx - x0) * height + (ty - y0), the
+            // enumeration order) when the window has at most 64 tiles — footprints up to 3 sigma = 48 px — so that
+            // the pair emission does not repeat the OBB / separating-axis tests (gsr_binning.cu); larger windows
+            // are flagged and re-tested there.
+            const int wx = x1 - x0, wy = y1 - y0;
+            const bool small = (wx * wy <= 64) & (x0 < 256) & (y0 < 256);
+            uint64_t hits = 0ull;
             for (int tx = x0; tx < x1; ++tx) {
                 const float left = __fmul_rn(__int2float_rn(tx), 16.0f);
                 const float right = __fmul_rn(__int2float_rn(tx + 1), 16.0f);
                 for (int ty = y0; ty < y1; ++ty) {
                     const float top = __fmul_rn(__int2float_rn(ty), 16.0f);
                     const float bottom = __fmul_rn(__int2float_rn(ty + 1), 16.0f);
-                    c += obb_hits_tile(ob, left, right, top, bottom) ? 1 : 0;
+                    if (obb_hits_tile(ob, left, right, top, bottom)) {
+                        ++c;
+                        if (small) hits |= 1ull << ((tx - x0) * wy + (ty - y0));
+                    }
                 }
+            }
+            if (tile_mask != nullptr) {
+                tile_mask[i] = hits;
+                tile_win[i] = small ? ((uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)wx << 16) | ((uint32_t)wy << 24))
+                                    : 0xffffffffu;
             }
             pk = (1ull << 32) | (uint64_t)(uint32_t)c;
         }
@@ -425,10 +441,12 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
                            const float* camera_centre, int H, int W, float near_thresh, float far_thresh,
                            float cull_mask_padding, float mh_dist, uint32_t depth_base, float* records,
                            uint32_t* depth_key,
-                           uint8_t* visible, uint64_t* scan, void* temp, size_t temp_bytes, void* stream) {
+                           uint8_t* visible, uint64_t* scan, uint64_t* tile_mask, uint32_t* tile_win, void* temp,
+                           size_t temp_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 0) return GSR_OK;
     if (temp_bytes < gsr_preprocess_temp_bytes(N)) return GSR_ERR_BAD_ARG;
+    if ((tile_mask == nullptr) != (tile_win == nullptr)) return GSR_ERR_BAD_ARG;
     size_t scan_bytes = 0;
     cub::DeviceScan::InclusiveSum((void*)nullptr, scan_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, N);
     uint64_t* packed = reinterpret_cast<uint64_t*>((char*)temp + align256(scan_bytes));
@@ -439,7 +457,7 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
     N, xyz, xyz_camera_frame, cam_first, quaternion, scale, opacity_logit, rgb_dc, sh_rest, camera_T_world, K, \
         camera_centre, (float)W, (float)H,                                                                 \
         near_thresh, far_thresh, cull_mask_padding, mh_dist, ntx, nty, depth_base, records, depth_key, visible, \
-        packed, use_tma
+        packed, tile_mask, tile_win, use_tma
     switch (n_sh_rest) {
         case 0: k_preprocess_fwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
         case 3: k_preprocess_fwd<4, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;

@@ -408,11 +408,14 @@ void render_depth_cuda(torch::Tensor xyz_camera_frame, torch::Tensor uvs, torch:
 #define F32PTR(t) ((t).data_ptr<float>())
 
 // returns (records[N,12], depth_key[N] i32-viewed u32, visible[N] u8, scan[N] i64-viewed u64)
-std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_preprocess_forward(
+// returns (records, depth_key, visible, scan, tile_mask, tile_win); the last two are empty unless with_tiles
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+fused_preprocess_forward_impl(
     torch::Tensor xyz, c10::optional<torch::Tensor> xyz_camera_frame, torch::Tensor quaternion, torch::Tensor scale,
     torch::Tensor opacity_logit, torch::Tensor rgb_dc, c10::optional<torch::Tensor> sh_rest,
     torch::Tensor camera_T_world, torch::Tensor K, c10::optional<torch::Tensor> camera_centre, int64_t H, int64_t W,
-    double near_thresh, double far_thresh, double cull_mask_padding, double mh_dist, int64_t depth_base) {
+    double near_thresh, double far_thresh, double cull_mask_padding, double mh_dist, int64_t depth_base,
+    bool with_tiles) {
     CHECK_VALID_INPUT(xyz); CHECK_VALID_INPUT(quaternion); CHECK_VALID_INPUT(scale); CHECK_VALID_INPUT(opacity_logit);
     CHECK_VALID_INPUT(rgb_dc); CHECK_VALID_INPUT(camera_T_world); CHECK_VALID_INPUT(K);
     CHECK_FLOAT_TENSOR(xyz); CHECK_FLOAT_TENSOR(quaternion); CHECK_FLOAT_TENSOR(scale);
@@ -456,6 +459,8 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
     torch::Tensor zkey = torch::empty({N}, opt.dtype(torch::kInt32));
     torch::Tensor visible = torch::empty({N}, opt.dtype(torch::kUInt8));
     torch::Tensor scan = torch::empty({N}, opt.dtype(torch::kInt64));
+    torch::Tensor tile_mask = torch::empty({with_tiles ? N : 0}, opt.dtype(torch::kInt64));
+    torch::Tensor tile_win = torch::empty({with_tiles ? N : 0}, opt.dtype(torch::kInt32));
     const size_t tb = gsr_preprocess_temp_bytes(N);
     torch::Tensor temp = torch::empty({(int64_t)tb}, opt.dtype(torch::kUInt8));
     check_rc(gsr_preprocess_forward(N, n_rest, F32PTR(xyz), cam_ptr, cam_first, F32PTR(quaternion), F32PTR(scale),
@@ -463,9 +468,34 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
                                     F32PTR(K), centre_ptr, (int)H, (int)W, (float)near_thresh, (float)far_thresh,
                                     (float)cull_mask_padding, (float)mh_dist, (uint32_t)depth_base, F32PTR(records),
                                     (uint32_t*)zkey.data_ptr<int>(), visible.data_ptr<uint8_t>(),
-                                    (uint64_t*)scan.data_ptr<int64_t>(), temp.data_ptr(), tb, cur_stream()),
+                                    (uint64_t*)scan.data_ptr<int64_t>(),
+                                    with_tiles && N > 0 ? (uint64_t*)tile_mask.data_ptr<int64_t>() : nullptr,
+                                    with_tiles && N > 0 ? (uint32_t*)tile_win.data_ptr<int>() : nullptr, temp.data_ptr(), tb,
+                                    cur_stream()),
              "gsr_preprocess_forward");
-    return std::make_tuple(records, zkey, visible, scan);
+    return std::make_tuple(records, zkey, visible, scan, tile_mask, tile_win);
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_preprocess_forward(
+    torch::Tensor xyz, c10::optional<torch::Tensor> xyz_camera_frame, torch::Tensor quaternion, torch::Tensor scale,
+    torch::Tensor opacity_logit, torch::Tensor rgb_dc, c10::optional<torch::Tensor> sh_rest,
+    torch::Tensor camera_T_world, torch::Tensor K, c10::optional<torch::Tensor> camera_centre, int64_t H, int64_t W,
+    double near_thresh, double far_thresh, double cull_mask_padding, double mh_dist, int64_t depth_base) {
+    auto r = fused_preprocess_forward_impl(xyz, xyz_camera_frame, quaternion, scale, opacity_logit, rgb_dc, sh_rest,
+                                           camera_T_world, K, camera_centre, H, W, near_thresh, far_thresh,
+                                           cull_mask_padding, mh_dist, depth_base, false);
+    return std::make_tuple(std::get<0>(r), std::get<1>(r), std::get<2>(r), std::get<3>(r));
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+fused_preprocess_forward_tiles(
+    torch::Tensor xyz, c10::optional<torch::Tensor> xyz_camera_frame, torch::Tensor quaternion, torch::Tensor scale,
+    torch::Tensor opacity_logit, torch::Tensor rgb_dc, c10::optional<torch::Tensor> sh_rest,
+    torch::Tensor camera_T_world, torch::Tensor K, c10::optional<torch::Tensor> camera_centre, int64_t H, int64_t W,
+    double near_thresh, double far_thresh, double cull_mask_padding, double mh_dist, int64_t depth_base) {
+    return fused_preprocess_forward_impl(xyz, xyz_camera_frame, quaternion, scale, opacity_logit, rgb_dc, sh_rest,
+                                         camera_T_world, K, camera_centre, H, W, near_thresh, far_thresh,
+                                         cull_mask_padding, mh_dist, depth_base, true);
 }
 
 // (M, P known) -> sorted gaussian ids [P] i32, tile ranges [n_tiles+1] i32, sorted record stream [P,12],
@@ -478,7 +508,12 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> fused_pre
 // returns (ids_sorted, ranges, stream_rec, vis_idx, uv, keys_sorted, id_bits)
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, int64_t> fused_bin(
     torch::Tensor records, torch::Tensor zkey, torch::Tensor visible, torch::Tensor scan, int64_t M, int64_t P,
-    int64_t H, int64_t W, double mh_dist, int64_t depth_bits, bool speculative, bool no_stream) {
+    int64_t H, int64_t W, double mh_dist, int64_t depth_bits, bool speculative, bool no_stream,
+    c10::optional<torch::Tensor> tile_mask, c10::optional<torch::Tensor> tile_win) {
+    const bool tiles = tile_mask.has_value() && tile_win.has_value() && tile_mask->numel() == records.size(0) &&
+                       tile_win->numel() == records.size(0) && records.size(0) > 0;
+    const uint64_t* tmask = tiles ? (const uint64_t*)tile_mask->data_ptr<int64_t>() : nullptr;
+    const uint32_t* twin = tiles ? (const uint32_t*)tile_win->data_ptr<int>() : nullptr;
     const int N = records.size(0);
     const int ntx = (W + 15) / 16, nty = (H + 15) / 16, n_tiles = ntx * nty;
     c10::cuda::CUDAGuard guard(records.device());
@@ -499,7 +534,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
     if (id_bits > 0) {  // (tile | depth | id) keys, keys-only radix sort
         check_rc(gsr_emit_keys(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(), visible.data_ptr<uint8_t>(),
                                (const uint64_t*)scan.data_ptr<int64_t>(), ntx, nty, (float)mh_dist, (int)depth_bits,
-                               id_bits, keys_a, vis_idx.data_ptr<int>(), F32PTR(uv), speculative ? P : 0,
+                               id_bits, keys_a, vis_idx.data_ptr<int>(), F32PTR(uv), speculative ? P : 0, tmask, twin,
                                cur_stream()),
                  "gsr_emit_keys");
         const size_t sb = gsr_sort_keys_temp_bytes((int)P);
@@ -519,7 +554,7 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Te
         check_rc(gsr_emit_pairs(N, F32PTR(records), (const uint32_t*)zkey.data_ptr<int>(),
                                 visible.data_ptr<uint8_t>(), (const uint64_t*)scan.data_ptr<int64_t>(), ntx, nty,
                                 (float)mh_dist, (int)depth_bits, keys_a, (uint32_t*)ids.data_ptr<int>(),
-                                vis_idx.data_ptr<int>(), F32PTR(uv), speculative ? P : 0, cur_stream()),
+                                vis_idx.data_ptr<int>(), F32PTR(uv), speculative ? P : 0, tmask, twin, cur_stream()),
                  "gsr_emit_pairs");
         const size_t sb = gsr_sort_pairs_temp_bytes((int)P);
         torch::Tensor temp = torch::empty({(int64_t)sb}, opt.dtype(torch::kUInt8));
@@ -846,6 +881,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("render_depth_cuda", &render_depth_cuda, "Render depth CUDA");
     // fused path
     m.def("fused_preprocess_forward", &fused_preprocess_forward, "fused per-gaussian stage");
+    m.def("fused_preprocess_forward_tiles", &fused_preprocess_forward_tiles,
+          "fused per-gaussian stage, also returning every gaussian's tile-hit mask and window");
     m.def("fused_bin", &fused_bin, "pair emission + radix sort + tile ranges + record stream");
     m.def("fused_render_forward", &fused_render_forward, "tile renderer forward on a record stream");
     m.def("fused_render_backward", &fused_render_backward, "tile renderer backward -> per-gaussian gradient slab");

@@ -55,6 +55,8 @@ USE_CONTRIBUTION_MASKS = os.environ.get("GSR_NO_MASKS", "0") != "1"
 # GSR_RECORD_STREAM=1 a separate kernel first writes the depth-sorted, tile-contiguous record stream they then read
 # with bulk copies (the round-1 arrangement)
 USE_RECORD_GATHER = os.environ.get("GSR_RECORD_STREAM", "0") != "1"
+# pair emission expands the tile-hit masks of the per-gaussian stage (GSR_RETEST_TILES=1: repeats the OBB tests)
+USE_TILE_MASKS = os.environ.get("GSR_RETEST_TILES", "0") != "1"
 IN_KERNEL_TRANSFORM_MIN_N = 16384
 CUBLAS_BATCH_CHUNK = 65535   # gridDim limit cuBLAS batches against
 SMALL_BATCH = 1024           # chunks below ~300 use another kernel (measured: 100 differs, 300 matches)
@@ -278,7 +280,8 @@ class _ProjectGaussians(torch.autograd.Function):
             else:
                 centre = torch.linalg.inv_ex(camera_T_world)[0][:3, 3].contiguous()
         with _stage(state, "preprocess_fwd"):
-            records, zkey, visible, scan = ext.fused_preprocess_forward(
+            # tile_mask / tile_win: the tiles each gaussian hits, tested once here and only expanded by the pair emission
+            records, zkey, visible, scan, tile_mask, tile_win = ext.fused_preprocess_forward_tiles(
                 xyz, xyz_cam, quaternion, scale, opacity_flat, rgb, sh, camera_T_world, K, centre, H, W, near, far,
                 pad, mh, depth_base)
         record_masks = USE_CONTRIBUTION_MASKS and any(ctx.needs_input_grad[:6])  # a backward pass can follow
@@ -297,7 +300,8 @@ class _ProjectGaussians(torch.autograd.Function):
 
         def bin_and_render(M_, P_, speculative):
             with _stage(state, "bin_sort_gather"):
-                binned = ext.fused_bin(records, zkey, visible, scan, M_, P_, H, W, mh, depth_bits, speculative, gather)
+                binned = ext.fused_bin(records, zkey, visible, scan, M_, P_, H, W, mh, depth_bits, speculative, gather,
+                                       tile_mask if USE_TILE_MASKS else None, tile_win if USE_TILE_MASKS else None)
             with _stage(state, "render_fwd"):
                 rendered = ext.fused_render_forward(records if gather else binned[2], binned[1], background, H, W, P_,
                                                     record_masks, binned[5], binned[0], binned[6], gather)

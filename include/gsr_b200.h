@@ -223,7 +223,12 @@ size_t gsr_preprocess_temp_bytes(int N);
  *                           bitlength(bits(far) - bits(near)) low bits are significant; 0 otherwise)
  *   visible  uint8 [N]      1 = survives the frustum cull (culling_mask = !visible)
  *   scan     uint64 [N]     INCLUSIVE scan of (visible << 32 | tiles_touched);
- *                           scan[N-1] >> 32 == M, scan[N-1] & 0xffffffff == P */
+ *                           scan[N-1] >> 32 == M, scan[N-1] & 0xffffffff == P
+ *   tile_mask uint64 [N], tile_win uint32 [N]  (both or neither; may be NULL): for visible gaussians whose tile
+ *                           window has at most 64 tiles, the tiles hit as a bit mask over the window (bit =
+ *                           (tx - x0) * height + (ty - y0)) and the window as x0 | y0 << 8 | width << 16 |
+ *                           height << 24; tile_win = 0xffffffff for larger windows.  gsr_emit_keys / gsr_emit_pairs
+ *                           expand the mask instead of repeating the OBB tests. */
 int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* xyz_camera_frame,
                            int cam_first, const float* quaternion,
                            const float* scale, const float* opacity_logit, const float* rgb_dc,
@@ -231,7 +236,8 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
                            const float* camera_centre, int H, int W, float near_thresh, float far_thresh,
                            float cull_mask_padding, float mh_dist, uint32_t depth_base, float* records,
                            uint32_t* depth_key,
-                           uint8_t* visible, uint64_t* scan, void* temp, size_t temp_bytes, void* stream);
+                           uint8_t* visible, uint64_t* scan, uint64_t* tile_mask, uint32_t* tile_win, void* temp,
+                           size_t temp_bytes, void* stream);
 
 /* emits the (tile, depth) keys and original-gaussian ids of all P pairs, the compact list of
  * visible gaussian ids vis_idx int32 [M] and the compacted uv [M,2] the reference returns */
@@ -243,7 +249,8 @@ int gsr_preprocess_forward(int N, int n_sh_rest, const float* xyz, const float* 
  * gsr_gather_records* are then called with `capacity` in place of P and ignore the padding. */
 int gsr_emit_pairs(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
                    const uint64_t* scan, int n_tiles_x, int n_tiles_y, float mh_dist, int depth_bits,
-                   uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, int64_t capacity, void* stream);
+                   uint64_t* keys, uint32_t* ids, int32_t* vis_idx, float* uv_compact, int64_t capacity,
+                   const uint64_t* tile_mask, const uint32_t* tile_win, void* stream);
 
 size_t gsr_sort_pairs_temp_bytes(int P);
 int gsr_sort_pairs(int P, int n_tiles, int depth_bits, const uint64_t* keys_in, const uint32_t* ids_in,
@@ -268,7 +275,8 @@ int gsr_gather_records(int P, const uint32_t* ids_sorted, const float* records, 
 int gsr_packed_id_bits(int N, int n_tiles, int depth_bits);
 int gsr_emit_keys(int N, const float* records, const uint32_t* depth_key, const uint8_t* visible,
                   const uint64_t* scan, int n_tiles_x, int n_tiles_y, float mh_dist, int depth_bits, int id_bits,
-                  uint64_t* keys, int32_t* vis_idx, float* uv_compact, int64_t capacity, void* stream);
+                  uint64_t* keys, int32_t* vis_idx, float* uv_compact, int64_t capacity, const uint64_t* tile_mask,
+                  const uint32_t* tile_win, void* stream);
 size_t gsr_sort_keys_temp_bytes(int P);
 int gsr_sort_keys(int P, int n_tiles, int depth_bits, int id_bits, const uint64_t* keys_in, uint64_t* keys_out,
                   void* temp, size_t temp_bytes, void* stream);

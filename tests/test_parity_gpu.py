@@ -410,6 +410,35 @@ def test_contribution_masks_do_not_change_the_gradients():
         assert rel(with_masks[k], without[k]) < 2e-5, (k, rel(with_masks[k], without[k]))  # fp32 atomics noise
 
 
+@pytest.mark.parametrize("sigma", [(1.2, 0.6, 0.3, 12.0), (14.0, 0.8, 2.0, 60.0)])
+def test_tile_hit_masks_and_retested_tiles_give_the_same_lists(sigma):
+    """The per-gaussian stage remembers which tiles of a gaussian's window it found hit (64-bit mask) and the pair
+    emission only expands that mask; windows of more than 64 tiles (the second scene: footprints up to 180 px) are
+    flagged and re-tested.  Either way the tile lists must be the ones GSR_RETEST_TILES=1 (re-test everything, the
+    round-1 arrangement) produces, bit for bit."""
+    from gaussian_splatting_b200 import rasterize as R
+
+    d = dev()
+    n = 60_000 if sigma[0] < 2 else 6_000
+    g = synth.make_gaussians(n, "720p", sh_degree=0, seed=12, device=d, sigma_px=sigma)
+    cam = synth.make_camera("720p", device=d)
+    T = synth.make_pose(1, 3, device=d)
+    bg = torch.full((3,), 0.5, device=d)
+    out = {}
+    for flag in (True, False):
+        R.USE_TILE_MASKS = flag
+        try:
+            with torch.no_grad():
+                image, mask, uv, st = rasterize(g, T, cam, 0.3, 500.0, 100, 3.0, True, bg, return_state=True)
+            out[flag] = (image, st.ranges.clone(), st.ids_sorted.clone(), st.P)
+        finally:
+            R.USE_TILE_MASKS = True
+    assert out[True][3] == out[False][3] and out[True][3] > 0
+    assert torch.equal(out[True][1], out[False][1]), "tile ranges differ"
+    assert torch.equal(out[True][2], out[False][2]), "sorted gaussian ids differ"
+    assert_bits_equal(out[True][0], out[False][0], "image")
+
+
 def test_record_gather_and_record_stream_agree():
     """Default: the tile kernels gather their records through the sorted keys with cp.async.  GSR_RECORD_STREAM=1:
     a separate kernel writes the tile-contiguous record stream they read with bulk copies.  Same records either way,
