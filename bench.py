@@ -239,17 +239,17 @@ def run_b200(args, rank, world, local):
     def step_e2e(i):
         main = torch.cuda.current_stream()
         zero_grads(g)
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(copy_stream):  # the forward's inputs first: nothing else delays its first kernel
             T_buf.copy_(poses_host[view_of(i)], non_blocking=True)
             K_buf.copy_(K_host, non_blocking=True)
             ev_small = copy_stream.record_event()
-            G_buf.copy_(G_host, non_blocking=True)
-            ev_grad = copy_stream.record_event()
         main.wait_event(ev_small)
         image, _, _ = rasterize(g, T_buf, cam_e2e, cfg["near_thresh"], cfg["far_thresh"],
                                 cfg["cull_mask_padding"], cfg["mh_dist"], True, bg)
         ev_img = main.record_event()
         with torch.cuda.stream(copy_stream):
+            G_buf.copy_(G_host, non_blocking=True)  # the backward's input: uploaded while the forward runs
+            ev_grad = copy_stream.record_event()
             copy_stream.wait_event(ev_img)
             image_host.copy_(image.detach(), non_blocking=True)
         main.wait_event(ev_grad)

@@ -137,6 +137,17 @@ def _note_pairs(key, P):
             del _PAIR_HISTORY[k]
 
 
+_SIDE = {}           # device index -> side stream for the count read-back
+
+
+def _side_stream(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE.get(idx)
+    if st is None:
+        st = _SIDE[idx] = torch.cuda.Stream(device=device)
+    return st
+
+
 def _pinned_slot(device):
     idx = device.index if device.index is not None else torch.cuda.current_device()
     ring = _PINNED.get(idx)
@@ -187,6 +198,10 @@ def native_centre_ok(device, n: int = 8, seed: int = 4321) -> bool:
     return same
 
 
+import functools
+
+
+@functools.lru_cache(maxsize=64)
 def _depth_key_params(near, far):
     """(base, bits): depth keys are float bits of z minus `base`; `bits` low bits are significant."""
     import math
@@ -321,10 +336,17 @@ class _ProjectGaussians(torch.autograd.Function):
             M, P = counts(total)
             binned, rendered = bin_and_render(M, P, False)
         else:
+            # the 8-byte copy goes on a side stream: on the main stream the binning kernels would queue behind it,
+            # and it is slow when the step's own host<->device traffic shares the copy engines (25 us, measured)
             slot = _pinned_slot(xyz.device)
-            slot.copy_(scan[-1:], non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record()
+            side = _side_stream(xyz.device)
+            scanned = torch.cuda.Event()
+            scanned.record()
+            with torch.cuda.stream(side):
+                side.wait_event(scanned)
+                slot.copy_(scan[-1:], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(side)
             binned, rendered = bin_and_render(N, cap, True)
             ready.synchronize()
             M, P = counts(int(slot.item()))
