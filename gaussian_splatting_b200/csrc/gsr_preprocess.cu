@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_BWD_MINB)
                      const float* __restrict__ camdev, const uint8_t* __restrict__ visible,
                      const float* __restrict__ g_rgb,
                      const float* __restrict__ g_opa, const float* __restrict__ g_uv,
-                     const float* __restrict__ g_conic, const float* __restrict__ g_uv_compact,
+                     const float* __restrict__ g_conic, const float* __restrict__ g_rows, int rows_uv,
+                     const float* __restrict__ g_uv_compact,
                      const uint64_t* __restrict__ scan, float* __restrict__ o_xyz,
                      float* __restrict__ o_quat, float* __restrict__ o_scale, float* __restrict__ o_opa,
                      float* __restrict__ o_dc, float* __restrict__ o_sh, int use_tma) {
@@ -324,19 +325,27 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_BWD_MINB)
         qw = quat[i * 4 + 0]; qx = quat[i * 4 + 1]; qy = quat[i * 4 + 2]; qz = quat[i * 4 + 3];
         s0 = scale[i * 3 + 0]; s1 = scale[i * 3 + 1]; s2 = scale[i * 3 + 2];
         opl = opa_logit[i];
+        if (g_rows != nullptr) {  // interleaved rows: rgb3 opa | uv2 conic0 conic1 | conic2 pad3
+            const float4* row = reinterpret_cast<const float4*>(g_rows + (size_t)i * GSR_GRAD_ROW_FLOATS);
+            const float4 r0 = row[0], r1 = row[1];
+            grv[0] = r0.x; grv[1] = r0.y; grv[2] = r0.z; gov = r0.w;
+            if (rows_uv) { guv[0] = r1.x; guv[1] = r1.y; }
+            gcv[0] = r1.z; gcv[1] = r1.w; gcv[2] = g_rows[(size_t)i * GSR_GRAD_ROW_FLOATS + 8];
+        } else {
         gcv[0] = g_conic[i * 3 + 0]; gcv[1] = g_conic[i * 3 + 1]; gcv[2] = g_conic[i * 3 + 2];
         // gradient on the projected mean = the render backward's sum (g_uv, by gaussian; may be absent) + whatever
         // arrives on the COMPACT uv rasterize returned (g_uv_compact [M,2]; row = rank among the visible gaussians,
         // read off the forward's packed inclusive scan)
         if (g_uv != nullptr) { guv[0] = g_uv[i * 2 + 0]; guv[1] = g_uv[i * 2 + 1]; }
+        gov = g_opa[i];
+        grv[0] = g_rgb[i * 3 + 0]; grv[1] = g_rgb[i * 3 + 1]; grv[2] = g_rgb[i * 3 + 2];
+        }
         if (g_uv_compact != nullptr) {
             const size_t r = (size_t)(scan[i] >> 32) - 1;
             const float2 t = *reinterpret_cast<const float2*>(g_uv_compact + r * 2);
             guv[0] = __fadd_rn(guv[0], t.x);
             guv[1] = __fadd_rn(guv[1], t.y);
         }
-        gov = g_opa[i];
-        grv[0] = g_rgb[i * 3 + 0]; grv[1] = g_rgb[i * 3 + 1]; grv[2] = g_rgb[i * 3 + 2];
     }
     load_view_cta(Tdev, Kdev, camdev, vc, HAS_SH);
     if (vis) {
@@ -476,6 +485,7 @@ int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float*
                             const float* K, const float* camera_centre, const uint8_t* visible,
                             const float* grad_rgb,
                             const float* grad_opacity, const float* grad_uv, const float* grad_conic,
+                            const float* grad_rows, int use_rows_uv,
                             const float* grad_uv_compact, const uint64_t* scan, float* g_xyz, float* g_quaternion, float* g_scale, float* g_opacity_logit,
                             float* g_rgb_dc, float* g_sh_rest, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -490,7 +500,7 @@ int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float*
 #define GSR_PRE_ARGS                                                                                   \
     N, xyz, quaternion, scale, opacity_logit, camera_T_world, K, camera_centre, visible, grad_rgb,         \
         grad_opacity, grad_uv,                                                                             \
-        grad_conic, grad_uv_compact, scan, g_xyz, g_quaternion, g_scale, g_opacity_logit, g_rgb_dc, g_sh_rest, use_tma
+        grad_conic, grad_rows, use_rows_uv, grad_uv_compact, scan, g_xyz, g_quaternion, g_scale, g_opacity_logit, g_rgb_dc, g_sh_rest, use_tma
     switch (n_sh_rest) {
         case 0: k_preprocess_bwd<1, false><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;
         case 3: k_preprocess_bwd<4, true><<<grid, block, 0, st>>>(GSR_PRE_ARGS); break;

@@ -620,7 +620,8 @@ torch::Tensor fused_render_backward(torch::Tensor grad_image, int64_t N, torch::
                     grad_image.size(2) == 3,
                 "grad_image must be HxWx3");
     c10::cuda::CUDAGuard guard(grad_image.device());
-    torch::Tensor slab = torch::zeros({N * 9}, grad_image.options());
+    // gather mode: interleaved rows [N,12] (vector reductions); stream mode: planar [9N]
+    torch::Tensor slab = torch::zeros({N * (gather ? (int64_t)GSR_GRAD_ROW_FLOATS : 9)}, grad_image.options());
     float* g_rgb = slab.data_ptr<float>();
     float* g_opa = g_rgb + (size_t)N * 3;
     float* g_uv = g_opa + (size_t)N;
@@ -632,7 +633,8 @@ torch::Tensor fused_render_backward(torch::Tensor grad_image, int64_t N, torch::
                                             by_key ? (const uint64_t*)keys_sorted->data_ptr<int64_t>() : nullptr, (int)id_bits,
                                             (!by_key && ids_sorted.numel() > 0) ? ids_sorted.data_ptr<int>() : nullptr,
                                             ranges.data_ptr<int>(), F32PTR(background), H, W, n.data_ptr<int>(), F32PTR(w),
-                                            F32PTR(grad_image), g_rgb, g_opa, g_uv, g_conic, mptr, cur_stream()),
+                                            F32PTR(grad_image), nullptr, nullptr, nullptr, nullptr, g_rgb, mptr,
+                                            cur_stream()),
                  "gsr_render_backward_gather");
     } else {
         check_rc(gsr_render_backward(F32PTR(stream_rec), ids_sorted.data_ptr<int>(), ranges.data_ptr<int>(),
@@ -658,7 +660,8 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
                                                      c10::optional<torch::Tensor> scan, bool use_slab_uv) {
     CHECK_VALID_INPUT(slab); CHECK_FLOAT_TENSOR(slab);
     const int64_t N = xyz.size(0);
-    TORCH_CHECK(slab.numel() == N * 9, "gradient slab must hold 9 floats per gaussian");
+    const bool rows = slab.numel() == N * (int64_t)GSR_GRAD_ROW_FLOATS && N > 0;  // interleaved [N,12] (else planar [9N])
+    TORCH_CHECK(rows || slab.numel() == N * 9, "gradient slab must hold 9 (planar) or 12 (rows) floats per gaussian");
     c10::cuda::CUDAGuard guard(xyz.device());
     auto opt = xyz.options();
     const float* g_rgb = slab.data_ptr<float>();
@@ -705,7 +708,8 @@ std::vector<torch::Tensor> fused_preprocess_backward(torch::Tensor slab, torch::
     check_rc(gsr_preprocess_backward((int)N, n_rest, F32PTR(xyz), F32PTR(quaternion), F32PTR(scale),
                                      F32PTR(opacity_logit), F32PTR(camera_T_world), F32PTR(K),
                                      camera_centre.has_value() ? camera_centre->data_ptr<float>() : nullptr,
-                                     visible.data_ptr<uint8_t>(), g_rgb, g_opa, g_uv, g_conic, g_uv_compact,
+                                     visible.data_ptr<uint8_t>(), g_rgb, g_opa, g_uv, g_conic,
+                                     rows ? slab.data_ptr<float>() : nullptr, use_slab_uv ? 1 : 0, g_uv_compact,
                                      scan_ptr, F32PTR(o_xyz),
                                      F32PTR(o_q), F32PTR(o_s), F32PTR(o_o), F32PTR(o_dc),
                                      n_rest ? F32PTR(g_sh) : nullptr, cur_stream()),

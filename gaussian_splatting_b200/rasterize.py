@@ -224,7 +224,7 @@ class _ViewState:
     """Non-differentiable per-view buffers shared by the two autograd nodes."""
 
     __slots__ = ("N", "M", "P", "H", "W", "visible", "vis_idx", "_ids_sorted", "ranges", "stream_rec", "gather",
-                 "records", "keys_sorted", "id_bits",
+                 "records", "keys_sorted", "id_bits", "slab_width",
                  "n_per_pixel", "w_per_pixel", "background", "profile", "grad_flat", "grad_out", "vis_idx32", "scan", "masks", "uv_ref", "uv_grad_emitted", "image", "speculation_overflowed")
 
     @property
@@ -366,7 +366,9 @@ class _ProjectGaussians(torch.autograd.Function):
         state.vis_idx = state.vis_idx32 = vis_idx                # int32 [M]: visible gaussians, ascending
         state._ids_sorted, state.ranges, state.stream_rec = ids_sorted, ranges, stream_rec
         state.scan = scan
-        carrier = torch.empty(9 * xyz.shape[0], dtype=xyz.dtype, device=xyz.device)
+        # gradient slab rows: 12 floats per gaussian (interleaved, gather mode) or 9 (planar, record-stream mode)
+        state.slab_width = 12 if gather else 9
+        carrier = torch.empty(state.slab_width * xyz.shape[0], dtype=xyz.dtype, device=xyz.device)
         ctx.state = state
         ctx.has_sh = sh is not None
         ctx.save_for_backward(xyz, quaternion, scale, opacity_flat, sh, camera_T_world, K, centre)
@@ -378,7 +380,7 @@ class _ProjectGaussians(torch.autograd.Function):
         st = ctx.state
         N = st.N
         if grad_carrier is None:
-            grad_carrier = torch.zeros(9 * N, dtype=xyz.dtype, device=xyz.device)
+            grad_carrier = torch.zeros(st.slab_width * N, dtype=xyz.dtype, device=xyz.device)
         slab = grad_carrier.contiguous()
         # Gradient on the projected means: the render backward's sums sit in the slab's uv section (by gaussian).
         # What autograd hands us for the COMPACT uv is either nothing / only what the caller added upstream of uv
@@ -426,7 +428,10 @@ class _CompositeTiles(torch.autograd.Function):
         if not watched:
             return None, slab, None, None
         N = st.N
-        grad_uv = slab[4 * N:6 * N].view(N, 2).index_select(0, st.vis_idx)
+        if st.slab_width == 12:   # interleaved rows: rgb3 opa | uv2 conic0 conic1 | conic2 pad3
+            grad_uv = slab.view(N, 12).index_select(0, st.vis_idx)[:, 4:6].contiguous()
+        else:                     # planar: rgb [N,3] | opacity [N] | uv [N,2] | conic [N,3]
+            grad_uv = slab[4 * N:6 * N].view(N, 2).index_select(0, st.vis_idx)
         return grad_uv, slab, None, None
 
 

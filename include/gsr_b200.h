@@ -164,11 +164,16 @@ int gsr_render_forward_gather(const float* gaussian_records, const uint64_t* key
                               const int32_t* ids_sorted, const int32_t* tile_ranges, const float* background_rgb, int H,
                               int W, int32_t* num_splats_per_pixel, float* final_weight_per_pixel, float* image,
                               uint32_t* contribution_masks, void* stream);
+/* Gradient destination: the four planar arrays (grad_rows NULL), or grad_rows [N, GSR_GRAD_ROW_FLOATS] (16-byte
+ * aligned, zero-filled; then the four planar pointers are ignored): one interleaved row per gaussian,
+ * rgb3 opacity | uv2 conic0 conic1 | conic2 pad3, accumulated with 16-byte vector reductions — the nine sums of a pair
+ * touch two adjacent 32-byte sectors instead of four arrays.  gsr_preprocess_backward reads either form. */
+#define GSR_GRAD_ROW_FLOATS 12
 int gsr_render_backward_gather(const float* gaussian_records, const uint64_t* keys_sorted, int id_bits,
                                const int32_t* ids_sorted, const int32_t* tile_ranges, const float* background_rgb, int H,
                                int W, const int32_t* num_splats_per_pixel, const float* final_weight_per_pixel,
                                const float* grad_image, float* grad_rgb, float* grad_opacity, float* grad_uv,
-                               float* grad_conic, const uint32_t* contribution_masks, void* stream);
+                               float* grad_conic, float* grad_rows, const uint32_t* contribution_masks, void* stream);
 
 /* General renderers: any dtype, any n_sh in {1,4,9,16} (per-pixel SH via view_dir_by_pixel
  * [H,W,3]); same semantics as the reference's template instantiations
@@ -289,11 +294,14 @@ int gsr_gather_records_keys(int P, int id_bits, const uint64_t* keys_sorted, con
  * mean is grad_uv[i] (skipped when grad_uv is NULL) PLUS grad_uv_compact[(scan[i] >> 32) - 1] (skipped when NULL):
  * grad_uv_compact [M,2] is a gradient on the compact uv rasterize returned, in its order (scan = the packed
  * inclusive scan of gsr_preprocess_forward) — what a caller added upstream of uv, or the total autograd hands over.
+ * grad_rows != NULL: the interleaved rows of gsr_render_backward_gather instead of the four planar arrays
+ * (grad_uv == NULL then still means "skip the render backward's uv sums").
  * Writes dense parameter gradients for all N gaussians (zeros for culled ones). */
 int gsr_preprocess_backward(int N, int n_sh_rest, const float* xyz, const float* quaternion,
                             const float* scale, const float* opacity_logit, const float* camera_T_world,
                             const float* K, const float* camera_centre, const uint8_t* visible, const float* grad_rgb,
                             const float* grad_opacity, const float* grad_uv, const float* grad_conic,
+                            const float* grad_rows, int use_rows_uv,
                             const float* grad_uv_compact, const uint64_t* scan, float* g_xyz, float* g_quaternion,
                             float* g_scale, float* g_opacity_logit, float* g_rgb_dc, float* g_sh_rest, void* stream);
 
