@@ -115,22 +115,23 @@ __global__ void __launch_bounds__(BIN_THREADS)
         // the enumeration order of walk_tiles: x-major, then y)
         uint64_t m = tile_mask[i];
         const int x0 = (int)(win & 0xffu), y0 = (int)((win >> 8) & 0xffu), wy = (int)(win >> 24);
-        const uint64_t z = zkey[i];
         const int64_t base = (int64_t)(prev & 0xffffffffu);
         const int64_t lim = cap > 0 ? cap : INT64_MAX;
-        int n = 0;
+        // key = tile << (depth_bits + id_bits) | low; everything below the tile field is the same for all pairs
+        const int tile_shift = depth_bits + id_bits;
+        const uint64_t low = (id_bits > 0) ? (((uint64_t)zkey[i] << id_bits) | (uint32_t)i) : (uint64_t)zkey[i];
+        // bit b = x * wy + y, ascending: the column is tracked incrementally — no division per pair
+        int n = 0, col0 = 0, tx = x0;
         while (m) {
             const int b = __ffsll((long long)m) - 1;
             m &= m - 1;
-            const int tx = x0 + b / wy, ty = y0 + b % wy;
+            while (b - col0 >= wy) {
+                col0 += wy;
+                ++tx;
+            }
             if (base + n < lim) {
-                const uint64_t k = ((uint64_t)(uint32_t)(ty * ntx + tx) << depth_bits) | z;
-                if (id_bits > 0) {
-                    keys[base + n] = (k << id_bits) | (uint32_t)i;
-                } else {
-                    keys[base + n] = k;
-                    ids[base + n] = (uint32_t)i;
-                }
+                keys[base + n] = ((uint64_t)(uint32_t)((y0 + b - col0) * ntx + tx) << tile_shift) | low;
+                if (id_bits == 0) ids[base + n] = (uint32_t)i;
             }
             ++n;
         }

@@ -13,10 +13,12 @@ Implementation: two autograd nodes around the native fused kernels
 (The tile renderer's forward kernel is enqueued by the projection node, right behind the binning and BEFORE the
 host reads the pair count; `_CompositeTiles` only ties its image into the graph.)
 
-``carrier`` is an uninitialised [9N] tensor that only carries gradient: the render backward
-returns its per-Gaussian sums (rgb, opacity, uv, conic) as the carrier's gradient, and the
-per-Gaussian backward consumes them.  One host sync per forward (to size the pair buffers);
-the reference path has ~25.
+``carrier`` is an uninitialised [12N] tensor ([9N] with the record stream) that only carries gradient: the
+render backward returns its per-Gaussian sums as the carrier's gradient — interleaved rows
+``rgb3 opacity | uv2 conic0 conic1 | conic2 pad3`` (planar rgb | opacity | uv | conic with the record stream) — and
+the per-Gaussian backward consumes them.  One host read per forward (the pair count, which sizes the pair
+buffers) and it is taken off the critical path: the buffers are sized from the previous views' counts and the
+count is only checked afterwards; the reference path has ~25 syncs.
 
 ``use_sh_precompute=False`` (per-pixel view directions) is routed through the operator-by-operator
 path `rasterize_unfused`, which mirrors the reference's structure on this library's operators.
