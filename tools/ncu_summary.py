@@ -60,7 +60,9 @@ def main():
         }
     Path(out).write_text(json.dumps(summary, indent=1))
     latest = Path(__file__).resolve().parents[1] / "profiles" / "ncu_traffic_latest.json"
-    latest.write_text(json.dumps(traffic, indent=1))
+    merged = json.loads(latest.read_text()) if latest.exists() else {}
+    merged.update(traffic)  # a report usually holds a subset of the kernels: keep the others' latest entries
+    latest.write_text(json.dumps(merged, indent=1))
     print(json.dumps(traffic, indent=1))
 
 
