@@ -162,3 +162,42 @@ def test_gradient_bucket_fallback_keeps_the_native_layout():
 
     with pytest.raises(ValueError):
         _Opt().step(packed)
+
+
+def test_depth_key_parameters_cover_the_degenerate_ranges():
+    """rasterize._depth_key_params: (base, bits) of the order-preserving depth key.  A usable positive range gives the
+    bit length of bits(far) - bits(near); anything else must fall back to the full 32-bit key, because depth_key()
+    sets bit 31 whenever the base is 0."""
+    import struct
+
+    from gaussian_splatting_b200.rasterize import _depth_key_params
+
+    def fbits(v):
+        return struct.unpack("<I", struct.pack("<f", v))[0]
+
+    base, bits = _depth_key_params(0.3, 500.0)
+    assert base == fbits(0.3) and bits == (fbits(500.0) - fbits(0.3)).bit_length() == 27
+    for near, far in ((0.0, 10.0), (-1.0, 10.0), (1e-50, 10.0), (0.3, float("inf")), (0.3, 1e39), (0.3, float("nan")),
+                      (5.0, 5.0), (7.0, 2.0)):
+        assert _depth_key_params(near, far) == (0, 32), (near, far)
+    assert _depth_key_params(1.0, 1.0000001)[1] >= 1
+
+
+def test_speculative_pair_capacity_follows_the_recent_views():
+    """rasterize._pair_capacity / _note_pairs: no history -> None (the first view of a kind reads the
+    count eagerly); otherwise max of the last 8 counts x headroom + 64 Ki, a multiple of 128, below 2^31."""
+    from gaussian_splatting_b200 import rasterize as R
+
+    key = ("test-key", 123)
+    R._PAIR_HISTORY.pop(key, None)
+    assert R._pair_capacity(key) is None
+    for p in (1000, 5_000_000, 4_000_000):
+        R._note_pairs(key, p)
+    cap = R._pair_capacity(key)
+    assert cap % 128 == 0 and cap >= int(5_000_000 * R.PAIR_HEADROOM) + 65536 and cap < 5_000_000 * 1.1 + 70000
+    for p in range(9):                      # the 5 M view drops out of the window of 8
+        R._note_pairs(key, 2_000_000 + p)
+    assert R._pair_capacity(key) < 3_000_000
+    R._note_pairs(key, 2**31 - 1)
+    assert R._pair_capacity(key) == 2**31 - 128
+    del R._PAIR_HISTORY[key]

@@ -60,3 +60,32 @@ def test_per_gaussian_kernels_stage_through_tma():
     fwd = find(counts, "k_preprocess_fwdILi16ELb1")
     bwd = find(counts, "k_preprocess_bwdILi16ELb1")
     assert fwd["UBLKCP"] >= 2 and bwd["UBLKCP"] >= 6   # SH slice in + records out; six gradient slices out
+
+
+def _tool_output(*args):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(exe).exists() or not LIB.exists():
+        pytest.skip("cuobjdump or the built library is missing")
+    return subprocess.run([exe, *args, str(LIB)], check=True, capture_output=True, text=True).stdout
+
+
+def test_render_backward_flushes_gradient_rows_with_vector_reductions():
+    """a (gaussian, tile) pair's nine sums leave as two 16-byte vector reductions
+    (red.global.add.v4.f32 -> SASS REDG.E.ADD.F32x4) + one scalar, not as nine scalar atomics."""
+    text = _tool_output("-sass")
+    body = text.split("Function : _ZN3gsr12k_render_bwdILb1ELb1E", 1)[1].split("Function :", 1)[0]
+    assert len(re.findall(r"REDG\.E\.ADD\.F32x4", body)) >= 2, "no 16-byte vector reductions in the gather backward"
+
+
+def test_render_kernels_keep_the_occupancy_design_md_states():
+    """the backward runs 8 CTAs per SM (<= 64 registers, <= 28 KB of shared memory per CTA), the
+    forward 9 (<= 56 registers); neither keeps arrays in local memory."""
+    text = _tool_output("--dump-resource-usage")
+    usage = {}
+    for name, line in re.findall(r"Function (\S+):\s*\n\s*(REG:.*)", text):
+        usage[name] = {k: int(v) for k, v in re.findall(r"([A-Z]+(?:\[0\])?):(\d+)", line)}
+    bwd = next(v for k, v in usage.items() if "k_render_bwdILb1ELb1E" in k)
+    fwd = next(v for k, v in usage.items() if "k_render_fwdILb1ELb1E" in k)
+    assert bwd["REG"] <= 64 and bwd["SHARED"] <= 28 * 1024 and bwd["STACK"] <= 16, bwd
+    assert fwd["REG"] <= 56 and fwd["SHARED"] <= 24 * 1024, fwd
+    assert 8 * (bwd["SHARED"] + 1024) <= 227 * 1024  # eight resident CTAs fit the SM's shared memory
