@@ -44,13 +44,13 @@ def main():
             T_buf.copy_(poses_host[i % 8], non_blocking=True)
             K_buf.copy_(K_host, non_blocking=True)
             ev_small = copy_stream.record_event()
-            G_buf.copy_(G_host, non_blocking=True)
-            ev_grad = copy_stream.record_event()
         main_s.wait_event(ev_small)
         image, _, _ = rasterize(g, T_buf, cam_e2e, cfg["near_thresh"], cfg["far_thresh"], cfg["cull_mask_padding"],
                                 cfg["mh_dist"], True, bg)
         ev_img = main_s.record_event()
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(copy_stream):  # same order as bench.py's step_e2e
+            G_buf.copy_(G_host, non_blocking=True)
+            ev_grad = copy_stream.record_event()
             copy_stream.wait_event(ev_img)
             image_host.copy_(image.detach(), non_blocking=True)
         main_s.wait_event(ev_grad)
