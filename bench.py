@@ -38,6 +38,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "fwd+bwd views/sec @1080p, 3M Gaussians, SH deg 3"
+# the workload both arms run (config.workload of every line)
+WORKLOAD = ("synthetic 3M Gaussians, 1080p, SH deg 3 (BASELINE.json configs[2]/[3]); one view per GPU per step, ring "
+            "of 8 poses (3 deg yaw steps), fwd + bwd of image against a fixed upstream gradient")
 N_GAUSS = 3_000_000
 RES = "1080p"
 SH_DEGREE = 3
@@ -367,9 +370,7 @@ def run_b200(args, rank, world, local):
         "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic 3M Gaussians, 1080p, SH deg 3 (BASELINE.json configs[2]/[3]); one view "
-                               "per GPU per step, ring of 8 poses (3 deg yaw steps), fwd + bwd of image against a "
-                               "fixed upstream gradient",
+        "config": {"workload": WORKLOAD,
                    "gaussians": N_GAUSS, "image": "1920x1080", "sh_degree": SH_DEGREE, "views_per_step": world,
                    "parallelism": f"views sharded 1 per GPU x{world}, gaussians replicated, no collective",
                    "view_schedule": "step i, rank r -> pose (i + r) mod 8",
@@ -533,7 +534,8 @@ def run_reference(args, rank, world, local):
         "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "synthetic 3M Gaussians, 1080p, SH deg 3; same scene/poses as the b200 arm",
+        "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "image": "1920x1080", "sh_degree": SH_DEGREE,
+                   "views_per_step": 1,
                    "how": "unmodified joeyan/gaussian_splatting: its CUDA extension compiled for sm_100 "
                           "(oracle/_ref) driven by its own splat_py.rasterize.rasterize + backward, on GPU 0",
                    "launched_world_size": world,
@@ -558,7 +560,7 @@ def run_reference_cpu(args, rank):
         "metric": METRIC, "value": cpu["value"], "unit": "views/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "synthetic 3M Gaussians, 1080p, SH deg 3 (bounded sample, see cpu_baseline.sample)"},
+        "config": {"workload": WORKLOAD + " (bounded sample, see cpu_baseline.sample)"},
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
